@@ -1,0 +1,128 @@
+/* rpgp.h -- C ABI of librpgp.so: the B200-native (sm_100a) matrix-free kernel-matrix multiply of
+ * Randomly-Projected-Additive-GPs and its quadratic-form derivative.
+ *
+ * This is the drop-in boundary of SURVEY.md §8(b).  The reference has no FFI of its own (it reaches the arithmetic
+ * through GPyTorch LazyTensors and PyKeOps); each entry point below names the reference interface it replaces
+ * (paths relative to the reference repository):
+ *
+ *   rpgp_mvm_fwd_f32      K.V as called by linear_cg: `KeOpsLazyTensor._matmul` / `SumLazyTensor._matmul`, built at
+ *                         gp_models/kernels/imq_kernel.py:32-58 (KeOps pattern), driven from
+ *                         training_routines.py:515-517,536-537 and fitting/optimizing.py:65-74
+ *   rpgp_quad_bwd_f32     `LazyTensor._quad_form_derivative(L, R)`; explicit-formula analogue
+ *                         gp_models/kernels/memory_efficient_gam_kernel.py:33-59 (GAMFunction.backward)
+ *   rpgp_project_f32      gp_models/kernels/scaled_projection_kernel.py:21-37 (ScaledProjectionKernel.forward) and
+ *                         gp_models/kernels/polynomial_projection_kernels.py:115-137 (_project)
+ *   rpgp_kernel_rows_f32  dense rows / blocks of K: gp_models/kernels/memory_efficient_gam_kernel.py:12-30
+ *                         (GAMFunction.forward), the pivoted-Cholesky row fetch and `diag`
+ *   rpgp_*_f64            the `--double` path (gp_experiment_runner.py:252,313-315; training_routines.py:481)
+ *   rpgp_kmv_host_f32     the whole path for host buffers: projection + K.V, as one call (what a ctypes/cffi
+ *                         binding inside the reference's kernel classes would use)
+ *
+ * Conventions
+ *   - all device pointers are borrowed for the duration of the (asynchronous) launch; nothing is retained.
+ *   - `stream` is a cudaStream_t passed as void*; no entry point synchronises except the *_host ones.
+ *   - every function returns 0 on success, otherwise an rpgp_status and rpgp_last_error() describes the failure
+ *     (the Python shim turns it into RuntimeError, mirroring the ValueError at memory_efficient_gam_kernel.py:15-16).
+ *   - "packed" coordinates: the n x (J*K) scaled projections Z^ are stored, pre-multiplied by sqrt(log2(e)/2), as
+ *     [nchunks][n][CP] float planes; chunk c holds projection groups c*G .. c*G+G-1, group g at columns
+ *     g*KP .. g*KP+K-1, zero padded.  rpgp_plan_layout() chooses (CP, nchunks, KP, G) for a given (J, K);
+ *     rpgp_pack_coords_f32 / rpgp_project_f32 write the layout.  Right-hand sides are [n][TP] float, zero padded,
+ *     TP = rpgp_padded_rhs(layout, t, backward).  `neg_log2c` is [nchunks*G] float: -log2(c_j), +inf for padding groups.
+ */
+#ifndef RPGP_H
+#define RPGP_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+typedef enum {
+    RPGP_OK = 0,
+    RPGP_ERR_INVALID = 1,
+    RPGP_ERR_CUDA = 2,
+    RPGP_ERR_UNSUPPORTED = 3,
+    RPGP_ERR_WORKSPACE = 4
+} rpgp_status;
+
+typedef struct {
+    int J, K;      /* projections, coordinates per projection */
+    int CP;        /* packed coordinates per chunk (multiple of 4, <= 32) */
+    int nchunks;   /* coordinate chunks */
+    int KP;        /* padded coordinates per group (1 when K == 1) */
+    int G;         /* groups per chunk */
+} rpgp_layout;
+
+int rpgp_version(void);
+const char* rpgp_last_error(void);
+
+/* layout planning ------------------------------------------------------------------------------------------------ */
+int rpgp_plan_layout(int J, int K, rpgp_layout* out);
+/* padded right-hand-side width TP the kernels are compiled for; 0 when t exceeds rpgp_max_rhs (chunk the columns) */
+int rpgp_padded_rhs(const rpgp_layout* lay, int t, int backward);
+int rpgp_max_rhs(const rpgp_layout* lay, int backward);
+double rpgp_coord_scale(void);            /* sqrt(log2(e)/2) */
+
+/* natural (n x J*K, row stride ld) float coordinates -> packed planes, multiplied by `scale` */
+int rpgp_pack_coords_f32(const float* Z, int64_t n, int64_t ld, const rpgp_layout* lay, float scale, float* Zp,
+                         void* stream);
+/* c (J floats, device) -> neg_log2c (nchunks*G floats, device) */
+int rpgp_pack_log2c_f32(const float* c, const rpgp_layout* lay, float* neg_log2c, void* stream);
+
+/* projection: Zp = pack( scale * post_inv[q] * sum_k X[i,k] * pre_inv[k] * W[q,k] ), FP64 accumulation.
+ * X: n x d (row stride ldx), W: (J*K) x d row-major (the torch.nn.Linear weight), pre_inv: d or NULL, post_inv: J*K
+ * or NULL (reciprocal lengthscales; prescale / postscale of scaled_projection_kernel.py:23-27). */
+int rpgp_project_f32(const float* X, int64_t n, int d, int64_t ldx, const float* W, const float* pre_inv,
+                     const float* post_inv, const rpgp_layout* lay, float scale, float* Zp, void* stream);
+
+/* forward K.V ---------------------------------------------------------------------------------------------------- */
+size_t rpgp_mvm_workspace_bytes(int64_t m, int64_t n, const rpgp_layout* lay, int t);
+/* out[i, 0..t) = sum_i' K[i,i'] V[i',:], i < m.  z1p: [nchunks][m][CP] with plane stride z1_stride (elements);
+ * z2p likewise with n.  Pass a row block of the packed planes (pointer + r0*CP, m = r1-r0, same plane stride) to
+ * compute the rows owned by one rank.  out: m x ldo. */
+int rpgp_mvm_fwd_f32(const float* z1p, int64_t m, int64_t z1_stride, const float* z2p, int64_t n, int64_t z2_stride,
+                     const rpgp_layout* lay, const float* neg_log2c, const float* Vp, int t, float* out, int ldo,
+                     void* workspace, size_t workspace_bytes, void* stream);
+
+/* quadratic-form derivative ------------------------------------------------------------------------------------------
+ * G = sum_col sum_{i,i'} Lrow[i,col] K[i,i'] Rcol[i',col].
+ *   dz1p[c][i][q] = dG / d z1p[c][i][q]   (packed, scaled coordinates)
+ *   g[c*G+g]      = sum_{i,i'} S[i,i'] k_g[i,i']   ( = dG / d ln c_g ;  dG / d neg_log2c = -ln2 * g )
+ * symmetric != 0: z1p is a row block of z2p itself (K(Z,Z)); Rrow / Lcol are then the R rows of the block and the
+ * full L, the returned dz1p is the TOTAL derivative w.r.t. the rows' coordinates (both roles) and g is this block's
+ * share of the full sum.  symmetric == 0: z1p / z2p independent, Rrow / Lcol ignored. */
+size_t rpgp_quad_workspace_bytes(int64_t m, int64_t n, const rpgp_layout* lay, int t);
+int rpgp_quad_bwd_f32(const float* z1p, int64_t m, int64_t z1_stride, const float* z2p, int64_t n, int64_t z2_stride,
+                      const rpgp_layout* lay, const float* neg_log2c, const float* Lrow, const float* Rrow,
+                      const float* Rcol, const float* Lcol, int t, int symmetric, float* dz1p, float* g,
+                      void* workspace, size_t workspace_bytes, void* stream);
+
+/* dense rows / blocks of K on natural (un-scaled) coordinates: out[p, i'] = K(Zr[p], Z2[i']); out: P x n */
+int rpgp_kernel_rows_f32(const float* Zr, int64_t P, const float* Z2, int64_t n, int64_t ld, int J, int K,
+                         const float* c, float* out, int64_t ldo, void* stream);
+
+/* FP64 path (natural coordinates, small n): same semantics, un-tiled */
+int rpgp_mvm_fwd_f64(const double* Z1, int64_t m, const double* Z2, int64_t n, int64_t ld, int J, int K,
+                     const double* c, const double* V, int t, double* out, void* stream);
+/* dZ1 (m x J*K, dense) and g (J) must be zeroed by the caller; contributions are accumulated */
+int rpgp_quad_bwd_f64(const double* Z1, int64_t m, const double* Z2, int64_t n, int64_t ld, int J, int K,
+                      const double* c, const double* L, const double* R, int t, double* dZ1, double* g, void* stream);
+int rpgp_kernel_rows_f64(const double* Zr, int64_t P, const double* Z2, int64_t n, int64_t ld, int J, int K,
+                         const double* c, double* out, int64_t ldo, void* stream);
+
+/* whole path on HOST buffers (allocates, copies H2D, projects, multiplies, copies D2H, synchronises):
+ * out = K(X1, X2) V + diag_add * V   (diag_add only applied when X1 == X2, i.e. X2 == NULL)
+ * X1: m x d, X2: n x d or NULL (=> X1), W: (J*K) x d, pre_inv: d or NULL, post_inv: J*K or NULL, c: J, V: n x t. */
+int rpgp_kmv_host_f32(const float* X1, int64_t m, const float* X2, int64_t n, int d, const float* W, int J, int K,
+                      const float* pre_inv, const float* post_inv, const float* c, const float* V, int t,
+                      float diag_add, float* out, int device);
+
+/* issue-rate microbenchmarks (roofline denominators): out[4*i..] = {fp32 lane-ops/clk/SM, mufu/clk/SM, ms, MHz} */
+int rpgp_measure_peaks(double* out, int max_ops, const char** names);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* RPGP_H */
