@@ -1,0 +1,378 @@
+#!/usr/bin/env python
+"""bench.py -- throughput of the K.V hot path (BASELINE.json metric: kernel-MVM pair-evals/s and CG-MLL iters/s).
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference] [--workload cfg4]
+    python -m torch.distributed.run --nnodes=1 --nproc-per-node N --master-addr 127.0.0.1 --master-port P bench.py --gpus N ...
+
+A "step" is one CG iteration of the exact-GP MLL solve at the named workload: one K^.P product with P in R^{n x t}
+(the fused sm_100a kernel, rows of K partitioned over the N ranks, NCCL all-gather of the row blocks) plus the O(n t)
+CG vector updates.  `value` = (i, i', j) pair-evaluations per second for the whole job (n*n*J per step), inputs
+resident in HBM.  `e2e` = the same metric through the host-buffer C-ABI entry point (rpgp_kmv_host_f32: H2D of X and V
+from pinned memory, projection, K.V, D2H of the product) every step.  `roofline` is the MUFU (XU-pipe ex2) roof the
+north star names, with the denominator measured live by the library's own microbenchmark (rpgp_measure_peaks); the
+HBM view (algorithmic bytes vs MEASURED_PEAKS.json) is reported beside it.  `cpu_baseline` / `--impl reference` time
+the C restatement of the reference's dense arithmetic (oracle/kmv_oracle.c) on the host cores, on a bounded row sample.
+"""
+import argparse
+import json
+import math
+import os
+import subprocess
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+PKG = os.path.join(ROOT, "randomly-projected-additive-gps_b200")
+for _p in (PKG, ROOT):
+    if _p not in sys.path:
+        sys.path.insert(0, _p)
+
+import numpy as np  # noqa: E402
+import torch  # noqa: E402
+
+WORKLOADS = {
+    # name: n, d, J, K, t, projection, c, description (BASELINE.json configs[i])
+    "cfg1": dict(n=2_000, d=10, J=20, K=1, t=11, proj="gaussian", desc="configs[0] n=2k d=10 additive_rp_J20_K1"),
+    "cfg2": dict(n=100_000, d=20, J=20, K=1, t=11, proj="gaussian", desc="configs[1] n=100k d=20 additive_rp_prescale_J20"),
+    "cfg3": dict(n=400_000, d=26, J=26, K=1, t=16, proj="spread", desc="configs[2] n=400k d=26 DPA-GP additive_spread_prescale_Jd t=16"),
+    "cfg4": dict(n=1_000_000, d=90, J=20, K=1, t=11, proj="gaussian", desc="configs[3] n=1M d=90 J=20 K=1 songs-shaped"),
+    "cfg5a": dict(n=1_000_000, d=90, J=1, K=20, t=11, proj="gaussian", desc="configs[4] n=1M d=90 J=1 K=20"),
+    "cfg5b": dict(n=1_000_000, d=90, J=20, K=5, t=11, proj="gaussian", desc="configs[4] n=1M d=90 J=20 K=5"),
+}
+
+
+def make_inputs(w, seed=0):
+    """Synthetic inputs of SURVEY.md §8(d): X ~ N(0,1), W from gen_rp (or diversified rows), ell = 1, c = ln2/J,
+    sigma_n^2 = 1, probes V column-normalised.  Host (pinned when CUDA is present) float32 tensors."""
+    import rp
+    torch.manual_seed(seed)
+    np.random.seed(seed)
+    n, d, J, K, t = w["n"], w["d"], w["J"], w["K"], w["t"]
+    X = torch.randn(n, d)
+    projs = [rp.gen_rp(d, K, "gaussian") for _ in range(J)]
+    W = torch.cat(projs, dim=1).t().contiguous()
+    if w["proj"] == "spread":
+        W, _ = rp.space_equally(W, lr=0.1, niter=5000)
+        W = W.contiguous()
+        c = torch.full((J,), math.log(2.0))                       # DPA-GP: no 1/J (training_routines.py:168)
+        inv_ell = torch.full((d,), 1.0 / math.log(2.0)) * 1.0     # base lengthscale softplus(0) folded into ell
+    else:
+        c = torch.full((J,), math.log(2.0) / J)
+        inv_ell = torch.ones(d)
+    V = torch.randn(n, t)
+    V = V / V.norm(dim=0, keepdim=True)
+    if torch.cuda.is_available():
+        X, V = X.pin_memory(), V.pin_memory()
+    return X, W, inv_ell, c, V
+
+
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons sampled every 200 ms during the timed region (B200_PROFILING.md)."""
+    Q = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+         "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index):
+        self.index, self.rows, self.proc = index, [], None
+
+    def __enter__(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.index), "--query-gpu=" + self.Q,
+                                          "--format=csv,noheader,nounits", "-lms", "200"],
+                                         stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            self.thread = threading.Thread(target=self._read, daemon=True)
+            self.thread.start()
+        except Exception:
+            self.proc = None
+        return self
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.rows.append([f.strip() for f in line.split(",")])
+
+    def __exit__(self, *exc):
+        if self.proc is not None:
+            self.proc.terminate()
+            try:
+                self.proc.wait(timeout=2)
+            except Exception:
+                self.proc.kill()
+
+    def summary(self):
+        sm, mx, reasons = [], 0.0, set()
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        for r in self.rows:
+            try:
+                sm.append(float(r[0]))
+                mx = max(mx, float(r[1]))
+                for name, flag in zip(names, r[3:7]):
+                    if flag.lower().startswith("active"):
+                        reasons.add(name)
+            except Exception:
+                continue
+        return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": mx or None,
+                "reasons": sorted(reasons), "samples": len(sm)}
+
+
+def dist_setup(gpus):
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    if world > 1:
+        import torch.distributed as dist
+        torch.cuda.set_device(local)
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+    return world, rank, local
+
+
+def cpu_sample_rate(Z, c, J, K, V, n, seconds=12.0, threads=0):
+    """Time the C oracle on a bounded row sample; returns (pair-evals/s, rows used, threads, seconds)."""
+    from oracle import c_oracle
+    threads = threads or c_oracle.max_threads()
+    quantum = 16 * threads                                      # kmv_oracle.c hands out 16-row blocks round-robin
+    probe_rows = min(n, 2 * quantum)
+    t0 = time.perf_counter()
+    c_oracle.kmv(Z[:probe_rows], Z, c, J, K, V, threads=threads)
+    dt = time.perf_counter() - t0
+    rate = probe_rows * n * J / dt
+    rows = int(min(n, max(probe_rows, rate * seconds / (n * J))))
+    rows = min(n, max(quantum, (rows // quantum) * quantum))
+    t0 = time.perf_counter()
+    c_oracle.kmv(Z[:rows], Z, c, J, K, V, threads=threads)
+    dt = time.perf_counter() - t0
+    return rows * n * J / dt, rows, threads, dt
+
+
+def run_reference(args, w):
+    """--impl reference: the reference's CPU arithmetic for the path (C port of the oracle: the reference is pure Python
+    over GPyTorch/KeOps and cannot be installed or compiled here -- DESIGN.md), all host threads, bounded sample."""
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    from oracle import c_oracle, rpgp_oracle as orc
+    X, W, inv_ell, c, V = make_inputs(w)
+    n, J, K = w["n"], w["J"], w["K"]
+    Z = orc.scaled_projection(X.numpy(), W.numpy(), 1.0 / inv_ell.numpy(), prescale=True, dtype=np.float32)
+    threads = c_oracle.max_threads()
+    quantum = 16 * threads                                      # kmv_oracle.c hands out 16-row blocks round-robin
+    probe_rows = min(n, 2 * quantum)
+    t0 = time.perf_counter()
+    c_oracle.kmv(Z[:probe_rows], Z, c.numpy(), J, K, V.numpy(), threads=threads)
+    rate = probe_rows * n * J / (time.perf_counter() - t0)
+    budget = 150.0 / max(1, args.steps + args.warmup)              # whole run within a few minutes
+    rows = int(min(n, max(quantum, rate * min(budget, 8.0) / (n * J))))
+    rows = min(n, max(quantum, (rows // quantum) * quantum))
+    for _ in range(args.warmup):
+        c_oracle.kmv(Z[:rows], Z, c.numpy(), J, K, V.numpy(), threads=threads)
+    t0 = time.perf_counter()
+    for _ in range(args.steps):
+        c_oracle.kmv(Z[:rows], Z, c.numpy(), J, K, V.numpy(), threads=threads)
+    dt = (time.perf_counter() - t0) / args.steps
+    value = rows * n * J / dt
+    sample = "%d of %d rows x all %d columns per step (extrapolates linearly in rows)" % (rows, n, n)
+    line = {
+        "impl": "reference", "metric": "kernel_mvm_pair_evals_per_s", "value": value, "unit": "pair-evals/s",
+        "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup, "ms_per_step": dt * 1e3,
+        "ms_per_full_step_extrapolated": dt * 1e3 * n / rows,
+        "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+        "config": {"workload": w["desc"], "n": n, "d": w["d"], "J": J, "K": K, "t": w["t"]},
+        "cpu_baseline": {"value": value, "unit": "pair-evals/s", "cores": threads, "kind": "port", "sample": sample},
+        "e2e": {"value": value, "unit": "pair-evals/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "cg_iters_per_s": 1.0 / (dt * n / rows), "gpu_launches": 0,
+    }
+    print(json.dumps(line), flush=True)
+
+
+def run_ours(args, w):
+    from rpgp import _lib
+    if not torch.cuda.is_available():
+        raise RuntimeError("bench.py (impl=ours) needs a CUDA device; the K.V path has no CPU fallback")
+    world, rank, local = dist_setup(args.gpus)
+    dev = torch.device("cuda", local)
+    torch.cuda.set_device(dev)
+    import torch.distributed as dist
+
+    n, d, J, K, t = w["n"], w["d"], w["J"], w["K"], w["t"]
+    X, W, inv_ell, c, V = make_inputs(w)
+    lay = _lib.plan_layout(J, K)
+    noise = 1.0
+
+    # row partition: rank r owns rows [r*blk, min(n, (r+1)*blk))
+    blk = (n + world - 1) // world
+    r0, r1 = min(n, rank * blk), min(n, (rank + 1) * blk)
+
+    Xd, Wd, Vd = X.to(dev, non_blocking=True), W.to(dev), V.to(dev, non_blocking=True)
+    zp = _lib.project(Xd, Wd, inv_ell.to(dev), None, lay)       # Z^ computed once per MLL step, before the CG loop
+    del Xd
+    nlc = _lib.pack_log2c(c.to(dev), lay)
+
+    # CG state (replicated on every rank, updated identically): solve K^ x = V
+    x = torch.zeros_like(Vd)
+    r = Vd.clone()
+    p = r.clone()
+    rz = (r * r).sum(0)
+    Kp_full = torch.empty((blk * world, t), device=dev)
+    kernel_events = []
+
+    def cg_iteration(record):
+        nonlocal rz, p
+        if record:
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            ev = (e0, e1)
+            kernel_events.append(ev)
+        else:
+            ev = None
+        Kp_blk = _lib.mvm_fwd(zp, zp, lay, nlc, p, row_range=(r0, r1), events=ev)
+        if world > 1:
+            if Kp_blk.shape[0] < blk:
+                Kp_blk = torch.cat([Kp_blk, Kp_blk.new_zeros((blk - Kp_blk.shape[0], t))])
+            dist.all_gather_into_tensor(Kp_full, Kp_blk.contiguous())
+            Kp = Kp_full[:n]
+        else:
+            Kp = Kp_blk
+        Kp = Kp + noise * p
+        alpha = rz / (p * Kp).sum(0).clamp_min(1e-30)
+        x.add_(p * alpha)
+        r.sub_(Kp * alpha)
+        rz_new = (r * r).sum(0)
+        p = r + p * (rz_new / rz.clamp_min(1e-30))
+        rz = rz_new
+
+    def sync():
+        torch.cuda.synchronize(dev)
+        if world > 1:
+            dist.barrier()
+            torch.cuda.synchronize(dev)
+
+    for _ in range(args.warmup):
+        cg_iteration(False)
+    sync()
+    launches0 = _lib.launch_count()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    with ClockSampler(local) as clocks:
+        e0.record()
+        for _ in range(args.steps):
+            cg_iteration(True)
+        e1.record()
+        sync()
+    launches = _lib.launch_count() - launches0
+    ms = torch.tensor([e0.elapsed_time(e1)], device=dev)
+    kms = torch.tensor([sum(a.elapsed_time(b) for a, b in kernel_events) / max(1, len(kernel_events))], device=dev)
+    if world > 1:
+        dist.all_reduce(ms, op=dist.ReduceOp.MAX)
+        dist.all_reduce(kms, op=dist.ReduceOp.MAX)
+    ms_per_step = float(ms.item()) / args.steps
+    kernel_ms = float(kms.item())
+    value = float(n) * n * J / (ms_per_step * 1e-3)
+
+    # ---- end-to-end through the host-buffer C ABI (every step: H2D X,V; project; K.V; D2H) ---------------------------
+    e2e = None
+    if not args.no_e2e:
+        Xn, Wn, Vn = X.numpy(), W.numpy(), V.numpy()
+        X1 = None if world == 1 else Xn[r0:r1]
+        def host_step():
+            if world == 1:
+                return _lib.kmv_host(Xn, None, Wn, J, K, inv_ell.numpy(), None, c.numpy(), Vn, diag_add=noise, device=local)
+            return _lib.kmv_host(X1, Xn, Wn, J, K, inv_ell.numpy(), None, c.numpy(), Vn, device=local)
+        host_step()
+        sync()
+        t0 = time.perf_counter()
+        for _ in range(args.e2e_steps):
+            host_step()
+        sync()
+        dt = torch.tensor([(time.perf_counter() - t0) / args.e2e_steps], device=dev, dtype=torch.float64)
+        if world > 1:
+            dist.all_reduce(dt, op=dist.ReduceOp.MAX)
+        m_rows = r1 - r0
+        h2d = 4 * ((n * d if world == 1 else (m_rows * d + n * d)) + J * K * d + d + J + n * t)
+        e2e = {"value": float(n) * n * J / float(dt.item()), "unit": "pair-evals/s", "ms_per_step": float(dt.item()) * 1e3,
+               "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": int(4 * m_rows * t),
+               "api": "rpgp_kmv_host_f32 (host buffers, pinned; projection + K.V + sigma^2 V)"}
+
+    if rank != 0:
+        if world > 1:
+            dist.barrier()
+            dist.destroy_process_group()
+        return
+
+    # ---- roofline: MUFU roof measured live by the library's own microbenchmark -------------------------------------------
+    peaks = _lib.measure_peaks()
+    sms = torch.cuda.get_device_properties(dev).multi_processor_count
+    mufu_peak = peaks["mufu_ex2"]["mufu_per_clk_sm"] * sms * peaks["mufu_ex2"]["mhz"] * 1e6
+    fp32_peak = peaks["ffma2"]["fp32_per_clk_sm"] * sms * peaks["ffma2"]["mhz"] * 1e6
+    m_rows = r1 - r0  # rank 0's block (largest)
+    groups = lay.nchunks * lay.G  # ex2 actually issued per pair (padding groups included)
+    ex2_alg = float(m_rows) * n * J
+    fp32_alg = float(m_rows) * n * ((3 * J + t) if K == 1 else (J * (2 * K + 1) + t))
+    ach = ex2_alg / (kernel_ms * 1e-3)
+    hbm_peak = None
+    try:
+        hbm_peak = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))["hbm_gbs"]
+    except Exception:
+        pass
+    alg_bytes = 4.0 * (m_rows * lay.nchunks * lay.CP + n * lay.nchunks * lay.CP + n * _lib.padded_rhs(lay, min(t, 16), False) + m_rows * t)
+    traffic = None
+    try:
+        traffic = json.load(open(os.path.join(ROOT, "profiles", "ncu_traffic.json"))).get(args.workload)
+    except Exception:
+        pass
+    roofline = {
+        "bound": "mufu", "achieved": ach / 1e12, "peak": mufu_peak / 1e12, "unit": "Tex2/s", "frac": ach / mufu_peak,
+        "peak_source": "measured live: rpgp_measure_peaks mufu_ex2 %.2f/clk/SM x %d SMs x %.0f MHz"
+                       % (peaks["mufu_ex2"]["mufu_per_clk_sm"], sms, peaks["mufu_ex2"]["mhz"]),
+        "kernel": "mvm_fwd_kernel<CP=%d,TP=%d,KP=%d,G=%d>" % (lay.CP, _lib.padded_rhs(lay, min(t, 16), False), lay.KP, lay.G),
+        "kernel_ms": kernel_ms, "kernel_share_of_step": kernel_ms / ms_per_step,
+        "algorithmic_ex2_per_launch": ex2_alg, "issued_ex2_per_launch": float(m_rows) * n * groups,
+        "fp32_frac": (fp32_alg / (kernel_ms * 1e-3)) / fp32_peak, "fp32_peak_Tlaneops": fp32_peak / 1e12,
+        "traffic": traffic,
+        "hbm": {"algorithmic_bytes_per_launch": alg_bytes, "achieved_GBps": alg_bytes / (kernel_ms * 1e-3) / 1e9,
+                "peak_GBps": hbm_peak, "frac": (alg_bytes / (kernel_ms * 1e-3) / 1e9 / hbm_peak) if hbm_peak else None,
+                "peak_source": "MEASURED_PEAKS.json" if hbm_peak else "absent"},
+    }
+
+    cpu = None
+    if not args.no_cpu_baseline:
+        from oracle import rpgp_oracle as orc
+        Z = orc.scaled_projection(X.numpy(), W.numpy(), 1.0 / inv_ell.numpy(), prescale=True, dtype=np.float32)
+        rate, rows, threads, secs = cpu_sample_rate(Z, c.numpy(), J, K, V.numpy(), n)
+        cpu = {"value": rate, "unit": "pair-evals/s", "cores": threads, "kind": "port",
+               "sample": "%d of %d rows x all %d columns, %.1f s (oracle/kmv_oracle.c, float32)" % (rows, n, n, secs)}
+
+    line = {
+        "metric": "kernel_mvm_pair_evals_per_s", "value": value, "unit": "pair-evals/s", "n_gpus": world,
+        "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms_per_step, "higher_is_better": True,
+        "scaling": "strong", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+        "config": {"workload": w["desc"], "n": n, "d": d, "J": J, "K": K, "t": t, "noise": noise,
+                   "parallelism": "rows of K over %d rank(s), NCCL all-gather per CG iteration" % world,
+                   "l2": "inputs larger than L2 (Z^ %.0f MB, V %.0f MB)" % (n * lay.nchunks * lay.CP * 4 / 1e6, n * t * 4 / 1e6)
+                   if n * lay.nchunks * lay.CP * 4 > 126e6 else "inputs fit in L2 (reused every step by design: Z^ is read n/256 times per launch)"},
+        "cg_iters_per_s": 1e3 / ms_per_step, "pairs_per_s": value / J,
+        "e2e": e2e, "gpu_launches": int(launches), "roofline": roofline, "cpu_baseline": cpu,
+        "clocks": clocks.summary(),
+    }
+    print(json.dumps(line), flush=True)
+    if world > 1:
+        dist.barrier()
+        dist.destroy_process_group()
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=3)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--workload", default="cfg4", choices=sorted(WORKLOADS))
+    ap.add_argument("--e2e-steps", type=int, default=2)
+    ap.add_argument("--no-e2e", action="store_true")
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    args = ap.parse_args()
+    w = WORKLOADS[args.workload]
+    if args.impl == "reference":
+        run_reference(args, w)
+    else:
+        run_ours(args, w)
+
+
+if __name__ == "__main__":
+    main()

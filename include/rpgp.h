@@ -57,6 +57,8 @@ typedef struct {
 
 int rpgp_version(void);
 const char* rpgp_last_error(void);
+/* number of CUDA kernels this library has launched so far in this process (bench.py `gpu_launches`) */
+unsigned long long rpgp_launch_count(void);
 
 /* layout planning ------------------------------------------------------------------------------------------------ */
 int rpgp_plan_layout(int J, int K, rpgp_layout* out);

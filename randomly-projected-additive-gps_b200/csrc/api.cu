@@ -60,6 +60,7 @@ extern "C" {
 int rpgp_version(void) { return 100; }
 const char* rpgp_last_error(void) { return rpgp::last_error(); }
 double rpgp_coord_scale(void) { return COORD_SCALE_D; }
+unsigned long long rpgp_launch_count(void) { return rpgp::launch_count(); }
 
 // TP actually compiled for (layout, t): forward K=1 {4,8,12,16,32}; backward K=1 {4,12,16}; K>1 {4,16}
 int rpgp_padded_rhs(const rpgp_layout* lay, int t, int backward) {

@@ -210,11 +210,13 @@ int launch_pack_coords(const float* Z, long long n, long long ld, const Layout& 
     const long long total = (long long)lay.nchunks * n * lay.CP;
     if (total == 0) return OK;
     pack_coords_kernel<<<blocks_for(total, 256), 256, 0, st>>>(Z, n, ld, lay, scale, Zp);
+    note_launch();
     return cuda_fail(cudaGetLastError(), "pack_coords_kernel");
 }
 int launch_pack_log2c(const float* c, const Layout& lay, float* nlc, cudaStream_t st) {
     const int total = lay.nchunks * lay.G;
     pack_log2c_kernel<<<(total + 127) / 128, 128, 0, st>>>(c, lay, nlc);
+    note_launch();
     return cuda_fail(cudaGetLastError(), "pack_log2c_kernel");
 }
 int launch_project(const float* X, long long n, int d, long long ldx, const float* W, const float* pre_inv,
@@ -229,6 +231,7 @@ int launch_project(const float* X, long long n, int d, long long ldx, const floa
     const long long nblocks = (n + 127) / 128;
     project_kernel<<<(unsigned)nblocks, 256, in_smem ? wbytes : 0, st>>>(X, n, d, ldx, W, pre_inv, post_inv, lay, scale,
                                                                         Zp, in_smem);
+    note_launch();
     return cuda_fail(cudaGetLastError(), "project_kernel");
 }
 int launch_rows_f32(const float* Zr, long long P, const float* Z2, long long n, long long ld, int J, int K,
@@ -239,6 +242,7 @@ int launch_rows_f32(const float* Zr, long long P, const float* Z2, long long n, 
         dim3 grid((unsigned)((n + 255) / 256), (unsigned)pc);
         kernel_rows_kernel<float><<<grid, 256, 0, st>>>(Zr + p0 * ld, pc, Z2, n, ld, J, K, c, out + p0 * ldo, ldo);
     }
+    note_launch();
     return cuda_fail(cudaGetLastError(), "kernel_rows_kernel<float>");
 }
 int launch_rows_f64(const double* Zr, long long P, const double* Z2, long long n, long long ld, int J, int K,
@@ -249,27 +253,32 @@ int launch_rows_f64(const double* Zr, long long P, const double* Z2, long long n
         dim3 grid((unsigned)((n + 255) / 256), (unsigned)pc);
         kernel_rows_kernel<double><<<grid, 256, 0, st>>>(Zr + p0 * ld, pc, Z2, n, ld, J, K, c, out + p0 * ldo, ldo);
     }
+    note_launch();
     return cuda_fail(cudaGetLastError(), "kernel_rows_kernel<double>");
 }
 int launch_reduce_partials(const float* partial, int nparts, long long m, int TP, int t, float* out, int ldo, cudaStream_t st) {
     const long long total = m * t;
     if (total == 0) return OK;
     reduce_partials_kernel<<<(unsigned)((total + 255) / 256), 256, 0, st>>>(partial, nparts, m, TP, t, out, ldo);
+    note_launch();
     return cuda_fail(cudaGetLastError(), "reduce_partials_kernel");
 }
 int launch_axpy_rows(float alpha, const float* V, int ldv, long long m, int t, float* out, int ldo, cudaStream_t st) {
     const long long total = m * t;
     if (total == 0) return OK;
     axpy_rows_kernel<<<(unsigned)((total + 255) / 256), 256, 0, st>>>(alpha, V, ldv, m, t, out, ldo);
+    note_launch();
     return cuda_fail(cudaGetLastError(), "axpy_rows_kernel");
 }
 int launch_reduce_dz(const float* dzp, int nsplits, long long plane, float scale, float* dz, cudaStream_t st) {
     if (plane == 0) return OK;
     reduce_dz_kernel<<<blocks_for(plane, 256), 256, 0, st>>>(dzp, nsplits, plane, scale, dz);
+    note_launch();
     return cuda_fail(cudaGetLastError(), "reduce_dz_kernel");
 }
 int launch_reduce_g(const float* gp, long long nctas, int width, float scale, float* g, cudaStream_t st) {
     reduce_g_kernel<<<(width + 127) / 128, 128, 0, st>>>(gp, nctas, width, scale, g);
+    note_launch();
     return cuda_fail(cudaGetLastError(), "reduce_g_kernel");
 }
 int launch_mvm_f64(const double* Z1, long long m, const double* Z2, long long n, long long ld, int J, int K,
@@ -279,6 +288,7 @@ int launch_mvm_f64(const double* Z1, long long m, const double* Z2, long long n,
         const int tc = (t - t0 < F64_TMAX) ? (t - t0) : F64_TMAX;
         mvm_fwd_f64_kernel<<<(unsigned)((m + 63) / 64), 64, 0, st>>>(Z1, m, Z2, n, ld, J, K, c, V, t, t0, tc, out);
     }
+    note_launch();
     return cuda_fail(cudaGetLastError(), "mvm_fwd_f64_kernel");
 }
 int launch_quad_f64(const double* Z1, long long m, const double* Z2, long long n, long long ld, int J, int K,
@@ -286,6 +296,7 @@ int launch_quad_f64(const double* Z1, long long m, const double* Z2, long long n
     if (m == 0) return OK;
     const long long total = m * J;
     quad_bwd_f64_kernel<<<(unsigned)((total + 63) / 64), 64, 0, st>>>(Z1, m, Z2, n, ld, J, K, c, L, R, t, dZ1, g);
+    note_launch();
     return cuda_fail(cudaGetLastError(), "quad_bwd_f64_kernel");
 }
 

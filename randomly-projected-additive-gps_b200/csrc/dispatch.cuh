@@ -35,6 +35,7 @@ inline int run_fwd(const MvmArgs& a, dim3 grid, cudaStream_t st) {
     constexpr size_t smem = fwd_smem_bytes<CP, TP>();
     if (int rc = set_smem(kernel, smem)) return rc;
     kernel<<<grid, ROWS_PER_CTA, smem, st>>>(a);
+    note_launch();
     return cuda_fail(cudaGetLastError(), "mvm_fwd_kernel launch");
 }
 
@@ -51,6 +52,7 @@ inline int run_grad(const GradArgs& a, dim3 grid, cudaStream_t st) {
         if (int rc = set_smem(kernel, smem)) return rc;
         kernel<<<grid, ROWS_PER_CTA, smem, st>>>(a);
     }
+    note_launch();
     return cuda_fail(cudaGetLastError(), "quad_rowgrad_kernel launch");
 }
 #endif

@@ -18,6 +18,8 @@ enum Status : int {
 
 void set_error(const char* fmt, ...);
 int cuda_fail(cudaError_t e, const char* what);
+void note_launch();                 // bump the library-wide kernel-launch counter
+unsigned long long launch_count();
 
 #define RPGP_CUDA_OK(call)                                                 \
     do {                                                                   \

@@ -31,6 +31,7 @@ class Layout(Structure):
 SIGNATURES = {
     "rpgp_version": (c_int, []),
     "rpgp_last_error": (c_char_p, []),
+    "rpgp_launch_count": (ctypes.c_ulonglong, []),
     "rpgp_plan_layout": (c_int, [c_int, c_int, POINTER(Layout)]),
     "rpgp_padded_rhs": (c_int, [POINTER(Layout), c_int, c_int]),
     "rpgp_max_rhs": (c_int, [POINTER(Layout), c_int]),
@@ -115,6 +116,10 @@ def plan_layout(J, K):
     return lay
 
 
+def launch_count():
+    return int(load().rpgp_launch_count())
+
+
 def coord_scale():
     return float(load().rpgp_coord_scale())
 
@@ -195,8 +200,9 @@ def pad_rhs(V, TP):
     return out
 
 
-def mvm_fwd(z1p, z2p, lay, nlc, V, row_range=None):
-    """out = K(z1 rows, z2) @ V for packed planes.  row_range=(r0, r1) restricts to a row block of z1p."""
+def mvm_fwd(z1p, z2p, lay, nlc, V, row_range=None, events=None):
+    """out = K(z1 rows, z2) @ V for packed planes.  row_range=(r0, r1) restricts to a row block of z1p.
+    events=(start, stop): optional torch.cuda.Event pair recorded tightly around the library call (kernel timing)."""
     require_cuda(z1p, z2p, nlc, V)
     assert z1p.dtype == torch.float32 and z2p.dtype == torch.float32 and V.dtype == torch.float32
     assert z1p.is_contiguous() and z2p.is_contiguous() and nlc.is_contiguous()
@@ -218,9 +224,13 @@ def mvm_fwd(z1p, z2p, lay, nlc, V, row_range=None):
             nbytes = lib.rpgp_mvm_workspace_bytes(m, n, ctypes.byref(lay), tc)
             ws, ws_bytes = _workspace(V.device, nbytes)
             o = out[:, t0:t0 + tc]
+            if events is not None and t0 == 0:
+                events[0].record()
             _check(lib.rpgp_mvm_fwd_f32(z1_ptr, m, m_full * lay.CP, _ptr(z2p), n, n * lay.CP, ctypes.byref(lay),
                                         _ptr(nlc), _ptr(Vp), tc, _ptr(o), out.stride(0), _ptr(ws), ws_bytes, st),
                    "rpgp_mvm_fwd_f32")
+        if events is not None:
+            events[1].record()
     return out
 
 
