@@ -84,7 +84,9 @@ class GeneralizedProjectionKernel(gpytorch.kernels.Kernel):
 
     def forward(self, x1, x2, **params):
         if (not self.learn_proj) and self.cache_proj:
-            if self.last_x1 is not None and torch.equal(x1, self.last_x1):
+            last = self.last_x1
+            if (last is not None and last.device == x1.device and last.dtype == x1.dtype and last.shape == x1.shape
+                    and torch.equal(x1, last)):
                 z1 = self.cached_projections
             else:
                 z1 = self._project(x1)

@@ -1,0 +1,77 @@
+"""CPU, world_size 2, gloo: the row partition and the one exchange of the K.V path (all-gather of row blocks per CG
+iteration, all-reduce of the outputscale partials), and that CG over a row-partitioned product is identical on every
+rank and equal to the single-process solve."""
+import os
+import socket
+
+import numpy as np
+import torch
+import torch.distributed as dist
+import torch.multiprocessing as mp
+
+from rpgp import dist as rdist
+from rpgp.solver import linear_cg
+
+
+def _free_port():
+    s = socket.socket()
+    s.bind(("127.0.0.1", 0))
+    port = s.getsockname()[1]
+    s.close()
+    return port
+
+
+def _worker(rank, world, port, n, out_path):
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    try:
+        g = torch.Generator().manual_seed(0)                      # replicated inputs: same seed on every rank
+        A = torch.randn(n, n, dtype=torch.float64, generator=g)
+        K = A @ A.t() / n + 2.0 * torch.eye(n, dtype=torch.float64)
+        rhs = torch.randn(n, 3, dtype=torch.float64, generator=g)
+        part = rdist.partition(n)
+        assert part.world == world and part.rank == rank
+        assert part.r0 == min(n, rank * part.block) and part.r1 == min(n, part.r0 + part.block)
+
+        def matmul(V):                                            # each rank multiplies only its rows, then all-gather
+            blk = K[part.r0:part.r1] @ V
+            return rdist.all_gather_rows(blk, part)
+
+        full = matmul(rhs)
+        assert torch.allclose(full, K @ rhs, atol=1e-12)
+        x = linear_cg(matmul, rhs, tolerance=1e-10, max_iter=500)
+        partial = torch.tensor([float(rank + 1), 2.0 * (rank + 1)], dtype=torch.float64)
+        total = rdist.all_reduce_sum(partial.clone())
+        assert torch.allclose(total, torch.tensor([3.0, 6.0], dtype=torch.float64))
+        gathered = [torch.empty_like(x) for _ in range(world)]
+        dist.all_gather(gathered, x)
+        assert all(torch.equal(gathered[0], t) for t in gathered)  # bit-identical CG state on every rank
+        if rank == 0:
+            np.save(out_path, x.numpy())
+        rdist.set_enabled(False)
+        assert rdist.world_size() == 1 and rdist.partition(n).r1 == n
+        rdist.set_enabled(True)
+    finally:
+        dist.destroy_process_group()
+
+
+def test_row_partition_allgather_and_cg_world2(tmp_path):
+    n = 101                                                       # uneven: blocks of 51 and 50 rows
+    out = str(tmp_path / "x.npy")
+    mp.spawn(_worker, args=(2, _free_port(), n, out), nprocs=2, join=True)
+    g = torch.Generator().manual_seed(0)
+    A = torch.randn(n, n, dtype=torch.float64, generator=g)
+    K = A @ A.t() / n + 2.0 * torch.eye(n, dtype=torch.float64)
+    rhs = torch.randn(n, 3, dtype=torch.float64, generator=g)
+    x_single = linear_cg(K.matmul, rhs, tolerance=1e-10, max_iter=500)
+    np.testing.assert_allclose(np.load(out), x_single.numpy(), rtol=1e-10, atol=1e-12)
+    np.testing.assert_allclose(np.load(out), torch.linalg.solve(K, rhs).numpy(), atol=1e-7)
+
+
+def test_partition_arithmetic():
+    p = rdist.Partition(10, 4, 3)
+    assert (p.block, p.r0, p.r1) == (3, 9, 10)
+    assert [rdist.Partition(10, 4, r).rows() for r in range(4)] == [(0, 3), (3, 6), (6, 9), (9, 10)]
+    assert rdist.Partition(2, 4, 3).rows() == (2, 2)              # more ranks than rows: empty block
+    assert rdist.partition(7).world == 1
