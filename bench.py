@@ -356,6 +356,60 @@ def run_ours(args, w):
         dist.destroy_process_group()
 
 
+def run_mll(args, w):
+    """--mode mll: one full training step through the reference-facing API -- model(X) -> -MLL -> backward (preconditioner,
+    multi-RHS CG with SLQ probes, fused gradient kernel) -- with the solver settings of the reference's large runs
+    (run_scripts/additive_spread_prescale_Jd.sh:6: --cg_tol 0.002).  Auxiliary line; the headline is the default mode."""
+    import training_routines as tr
+    from rpgp import _lib, gp as gpytorch
+    import importlib
+    cg_mod = importlib.import_module("rpgp.solver.linear_cg")   # the module (rpgp.solver re-exports the function under the same name)
+    dev = torch.device("cuda", int(os.environ.get("LOCAL_RANK", "0")))
+    world, rank, local = dist_setup(args.gpus)
+    torch.manual_seed(0)
+    np.random.seed(0)
+    n, d, J, K = w["n"], w["d"], w["J"], w["K"]
+    X = torch.randn(n, d, device=dev)
+    wtrue = torch.randn(d, 8, device=dev) / math.sqrt(d)
+    y = torch.sin(X @ wtrue).sum(-1) + 0.1 * torch.randn(n, device=dev)
+    y = (y - y.mean()) / y.std()
+    kw = dict(J=J, k=K, noise_prior=True, kernel_type="RBF", learn_proj=False, prescale=True, batch_kernel=(K == 1))
+    if w["proj"] == "spread":
+        kw.update(space_proj=True, batch_kernel=False, mem_efficient=True)
+    model, lik = tr.create_exact_gp(X, y, "additive_rp", **kw)
+    model = model.to(dev)
+    mll = gpytorch.mlls.ExactMarginalLogLikelihood(lik, model)
+    model.train()
+
+    def step():
+        model.zero_grad()
+        loss = -mll(model(X), y)
+        loss.backward()
+        return loss
+
+    import warnings
+    with gpytorch.settings.cg_tolerance(args.cg_tol), gpytorch.settings.max_cg_iterations(10_000), warnings.catch_warnings():
+        warnings.simplefilter("ignore")
+        for _ in range(args.warmup):
+            step()
+        torch.cuda.synchronize(dev)
+        it0, l0 = cg_mod.STATS["iterations"], _lib.launch_count()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for _ in range(args.steps):
+            loss = step()
+        e1.record()
+        torch.cuda.synchronize(dev)
+    ms = e0.elapsed_time(e1) / args.steps
+    iters = (cg_mod.STATS["iterations"] - it0) / args.steps
+    if rank == 0:
+        print(json.dumps({"metric": "mll_grad_step", "ms_per_step": ms, "cg_iterations_per_step": iters,
+                          "cg_iters_per_s": iters / (ms * 1e-3), "pair_evals_per_s": (iters + 3) * float(n) * n * J / (ms * 1e-3),
+                          "loss": float(loss), "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
+                          "gpu_launches": _lib.launch_count() - l0, "cg_tol": args.cg_tol,
+                          "config": {"workload": w["desc"], "n": n, "d": d, "J": J, "K": K, "t": 11}}), flush=True)
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
@@ -366,8 +420,12 @@ def main():
     ap.add_argument("--e2e-steps", type=int, default=2)
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--mode", default="cg", choices=["cg", "mll"], help="cg: one CG iteration per step (headline); mll: full MLL+gradient step")
+    ap.add_argument("--cg-tol", type=float, default=0.002)
     args = ap.parse_args()
     w = WORKLOADS[args.workload]
+    if args.mode == "mll" and args.impl == "ours":
+        return run_mll(args, w)
     if args.impl == "reference":
         run_reference(args, w)
     else:

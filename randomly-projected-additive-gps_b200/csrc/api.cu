@@ -2,6 +2,7 @@
 // grid/split selection, workspace carving and the host-buffer variant of the whole path.
 #include <algorithm>
 #include <cmath>
+#include <cstdlib>
 #include <cstring>
 #include <vector>
 
@@ -179,7 +180,12 @@ int rpgp_mvm_fwd_f32(const float* z1p, int64_t m, int64_t z1_stride, const float
         }
     }
     dim3 grid((unsigned)sp.row_blocks, (unsigned)sp.nsplits, (unsigned)lay->nchunks);
-    int rc = (lay->K == 1) ? launch_fwd_k1(lay->CP, TP, a, grid, st) : launch_fwd_kn(lay->KP, lay->G, lay->CP, TP, a, grid, st);
+    // RPGP_POLY_PAIRS overrides the number of projection pairs evaluated on the FMA pipe (tools/poly_sweep.py); -1 = default
+    static const int poly_env = [] { const char* e = getenv("RPGP_POLY_PAIRS"); return e ? atoi(e) : -1; }();
+    const int poly_pairs = (lay->K == 1) ? (poly_env >= 0 ? poly_env : default_poly_pairs(lay->CP, TP)) : 0;
+    int rc;
+    if (lay->K == 1 && poly_pairs > 0) rc = launch_fwd_k1_poly(lay->CP, TP, poly_pairs, a, grid, st);
+    else rc = (lay->K == 1) ? launch_fwd_k1(lay->CP, TP, a, grid, st) : launch_fwd_kn(lay->KP, lay->G, lay->CP, TP, a, grid, st);
     if (rc) return rc;
     if (!a.direct) return launch_reduce_partials(a.partial, (int)nparts, m, TP, t, out, ldo, st);
     return OK;

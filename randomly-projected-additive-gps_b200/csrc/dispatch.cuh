@@ -15,6 +15,15 @@ namespace rpgp {
     X(24, 1, 24, TP) X(32, 1, 32, TP)
 
 int launch_fwd_k1(int CP, int TP, const MvmArgs& a, dim3 grid, cudaStream_t st);
+int launch_fwd_k1_poly(int CP, int TP, int NP2, const MvmArgs& a, dim3 grid, cudaStream_t st);  // FMA-pipe exp2 variants
+
+// Packed projection pairs per (i,i') whose exponential goes to the FMA/ALU pipes instead of MUFU.  Measured on B200
+// (tools/poly_sweep.py, profiles/poly_sweep_r01.txt): an FFMA2 occupies two issue cycles, so the optimum is where
+// MUFU time 8*(CP - 2*NP2) meets the issue budget ~ (73 + 20 + 8 + 18*NP2 ...) -- about 20 % of the pairs at t <= 16.
+inline int default_poly_pairs(int CP, int TP) {
+    if (TP > 16) return 0;
+    return CP >= 28 ? 3 : (CP >= 16 ? 2 : (CP >= 8 ? 1 : 0));
+}
 int launch_fwd_kn(int KP, int G, int CP, int TP, const MvmArgs& a, dim3 grid, cudaStream_t st);
 int launch_grad_k1(int CP, int TP, const GradArgs& a, dim3 grid, cudaStream_t st);
 int launch_grad_kn(int KP, int G, int CP, int TP, const GradArgs& a, dim3 grid, cudaStream_t st);
@@ -29,9 +38,9 @@ inline int set_smem(KernelT kernel, size_t bytes) {
     return OK;
 }
 
-template <int CP, int TP, int KP, int G>
+template <int CP, int TP, int KP, int G, int NP2 = 0>
 inline int run_fwd(const MvmArgs& a, dim3 grid, cudaStream_t st) {
-    auto kernel = mvm_fwd_kernel<CP, TP, KP, G>;
+    auto kernel = mvm_fwd_kernel<CP, TP, KP, G, NP2>;
     constexpr size_t smem = fwd_smem_bytes<CP, TP>();
     if (int rc = set_smem(kernel, smem)) return rc;
     kernel<<<grid, ROWS_PER_CTA, smem, st>>>(a);

@@ -73,7 +73,40 @@ struct RowCoords {
     float cg[(KP == 1) ? 1 : G];          // K>1: -log2c per group
 };
 
-template <int CP, int KP, int G>
+// 2^(-u) for a packed pair on the FMA + ALU pipes instead of the XU pipe (takes load off MUFU, the binding unit):
+// Cody-Waite split with the 1.5*2^23 magic constant (round-to-nearest integer n, |f| <= 1/2), degree-5 minimax polynomial
+// for 2^f (max relative error 7.6e-8, i.e. the accuracy of ex2.approx), exponent inserted by an integer shift-add.
+// u is clamped to <= 126 so that the biased exponent cannot wrap (results below 2^-126 flush towards 0 like .ftz).
+__device__ __forceinline__ f32x2 exp2_neg_poly2(f32x2 u) {
+    const f32x2 MAGIC = pack2(12582912.f, 12582912.f);
+    // coefficients of q(g) = 2^(-g), g = -f  (odd powers negated)
+    const f32x2 C5 = pack2(-0.0013280353741720319f, -0.0013280353741720319f);
+    const f32x2 C4 = pack2(0.009675574488937855f, 0.009675574488937855f);
+    const f32x2 C3 = pack2(-0.05550701171159744f, -0.05550701171159744f);
+    const f32x2 C2 = pack2(0.24022118747234344f, 0.24022118747234344f);
+    const f32x2 C1 = pack2(-0.6931470036506653f, -0.6931470036506653f);
+    const f32x2 C0 = pack2(1.0000001192092896f, 1.0000001192092896f);
+    float ul, uh;
+    unpack2(u, ul, uh);
+    u = pack2(fminf(ul, 126.f), fminf(uh, 126.f));
+    const f32x2 rr = sub2(MAGIC, u);          // magic + x, x = -u : low mantissa bits hold n = round(x)
+    const f32x2 nn = sub2(rr, MAGIC);         // n as float
+    const f32x2 g = add2(u, nn);              // g = -(x - n) = -f
+    f32x2 acc = fma2(C5, g, C4);
+    acc = fma2(acc, g, C3);
+    acc = fma2(acc, g, C2);
+    acc = fma2(acc, g, C1);
+    acc = fma2(acc, g, C0);
+    float pl, ph, rl, rh;
+    unpack2(acc, pl, ph);
+    unpack2(rr, rl, rh);
+    const float el = __int_as_float(__float_as_int(pl) + (__float_as_int(rl) << 23));
+    const float eh = __int_as_float(__float_as_int(ph) + (__float_as_int(rh) << 23));
+    return pack2(el, eh);
+}
+
+// NP2 = number of packed projection pairs per (i,i') whose exponential is evaluated by exp2_neg_poly2 (K = 1 only)
+template <int CP, int KP, int G, int NP2 = 0>
 __device__ __forceinline__ float pair_kernel_value(const RowCoords<CP, KP, G>& r, const float* __restrict__ zcol) {
     // zcol: CP floats of one column in shared memory (16 B aligned)
     f32x2 zj[CP / 2];
@@ -89,9 +122,14 @@ __device__ __forceinline__ float pair_kernel_value(const RowCoords<CP, KP, G>& r
         for (int q = 0; q < CP / 2; ++q) {
             const f32x2 d = sub2(r.z[q], zj[q]);
             const f32x2 u = fma2(d, d, r.c2[q]);         // d^2 - log2c
-            float ul, uh;
-            unpack2(u, ul, uh);
-            const f32x2 e = pack2(ex2_ftz(-ul), ex2_ftz(-uh));
+            f32x2 e;
+            if (q >= CP / 2 - NP2) {
+                e = exp2_neg_poly2(u);
+            } else {
+                float ul, uh;
+                unpack2(u, ul, uh);
+                e = pack2(ex2_ftz(-ul), ex2_ftz(-uh));
+            }
             if (q & 1) s1 = add2(s1, e); else s0 = add2(s0, e);
         }
         float lo, hi;
@@ -138,7 +176,7 @@ __device__ __forceinline__ void load_row_coords(RowCoords<CP, KP, G>& r, const f
 template <int CP, int TP>
 constexpr size_t fwd_smem_bytes() { return 128 + (size_t)NSTAGE * TN * (CP + TP) * sizeof(float); }
 
-template <int CP, int TP, int KP, int G>
+template <int CP, int TP, int KP, int G, int NP2 = 0>
 __global__ void __launch_bounds__(ROWS_PER_CTA, 2) mvm_fwd_kernel(const MvmArgs a) {
     static_assert(CP % 4 == 0 && TP % 4 == 0, "packed layouts (16 B rows for the bulk copies)");
     static_assert(KP == 1 || (KP % 2 == 0 && G * KP <= CP), "group layout");
@@ -195,7 +233,7 @@ __global__ void __launch_bounds__(ROWS_PER_CTA, 2) mvm_fwd_kernel(const MvmArgs 
         for (int q = 0; q < TP / 2; ++q) lo[q] = 0ull;
 #pragma unroll 2
         for (int c = 0; c < cols; ++c) {
-            const float sv = pair_kernel_value<CP, KP, G>(r, zt + c * CP);
+            const float sv = pair_kernel_value<CP, KP, G, NP2>(r, zt + c * CP);
             const f32x2 ss = pack2(sv, sv);
 #pragma unroll
             for (int q = 0; q < TP / 4; ++q) {

@@ -21,6 +21,10 @@ class NumericalWarning(RuntimeWarning):
     pass
 
 
+# running totals since import (bench.py reads them to report CG iterations per second)
+STATS = {"solves": 0, "iterations": 0, "matmuls": 0}
+
+
 def linear_cg(matmul_closure, rhs, n_tridiag=0, tolerance=1.0, eps=None, stop_updating_after=None, max_iter=1000,
               max_tridiag_iter=20, initial_guess=None, preconditioner=None, return_info=False):
     """Solve A X = rhs for the columns of rhs (n x t).  Returns X, or (X, T) with T (n_tridiag, k, k) when n_tridiag > 0.
@@ -120,6 +124,9 @@ def linear_cg(matmul_closure, rhs, n_tridiag=0, tolerance=1.0, eps=None, stop_up
             tolerance_reached = True
             break
 
+    STATS["solves"] += 1
+    STATS["iterations"] += k + 1
+    STATS["matmuls"] += k + 2
     result = result * rhs_norm
     if not tolerance_reached and n_iter > 0:
         warnings.warn(
