@@ -88,6 +88,19 @@ int rpgp_mvm_fwd_f32(const float* z1p, int64_t m, int64_t z1_stride, const float
                      const rpgp_layout* lay, const float* neg_log2c, const float* Vp, int t, float* out, int ldo,
                      void* workspace, size_t workspace_bytes, void* stream);
 
+/* symmetric forward K(Z,Z).V on the tensor cores ---------------------------------------------------------------------
+ * Every kernel value is evaluated once and used for both out[i] and out[i'] (tcgen05, 3xTF32 split, FP64 global
+ * accumulation); K == 1, J <= 32, t <= 16 (rpgp_mvm_sym_supported).  Vp16: [n][16] zero-padded right-hand sides.
+ * Row blocks are 128 rows; a launch handles the unique block pairs owned by row blocks [row_block_begin, row_block_end)
+ * and writes their contributions to ALL n rows of out -- with the full range [0, ceil(n/128)) out is K.V, with a
+ * sub-range (one rank of a multi-GPU job) the outputs of the ranks must be summed (all-reduce).
+ * Accumulation uses FP64 atomics, so results are reproducible to FP32 rounding but not bit-identical run to run. */
+size_t rpgp_mvm_sym_workspace_bytes(int64_t n, const rpgp_layout* lay);
+int rpgp_mvm_sym_supported(const rpgp_layout* lay, int t);
+int rpgp_mvm_sym_f32(const float* zp, int64_t n, const rpgp_layout* lay, const float* neg_log2c, const float* Vp16, int t,
+                     float* out, int ldo, int row_block_begin, int row_block_end, void* workspace, size_t workspace_bytes,
+                     void* stream);
+
 /* quadratic-form derivative ------------------------------------------------------------------------------------------
  * G = sum_col sum_{i,i'} Lrow[i,col] K[i,i'] Rcol[i',col].
  *   dz1p[c][i][q] = dG / d z1p[c][i][q]   (packed, scaled coordinates)

@@ -9,6 +9,7 @@
 #include "../../include/rpgp.h"
 #include "aux_kernels.cuh"
 #include "dispatch.cuh"
+#include "sym_tc.cuh"
 
 namespace rpgp {
 const char* last_error();
@@ -189,6 +190,30 @@ int rpgp_mvm_fwd_f32(const float* z1p, int64_t m, int64_t z1_stride, const float
     if (rc) return rc;
     if (!a.direct) return launch_reduce_partials(a.partial, (int)nparts, m, TP, t, out, ldo, st);
     return OK;
+}
+
+size_t rpgp_mvm_sym_workspace_bytes(int64_t n, const rpgp_layout* lay) {
+    if (!lay || n <= 0) return 0;
+    return sym_workspace_bytes(n);
+}
+
+int rpgp_mvm_sym_supported(const rpgp_layout* lay, int t) {
+    return lay && lay->K == 1 && lay->nchunks == 1 && t >= 1 && t <= 16;
+}
+
+int rpgp_mvm_sym_f32(const float* zp, int64_t n, const rpgp_layout* lay, const float* neg_log2c, const float* Vp16, int t,
+                     float* out, int ldo, int row_block_begin, int row_block_end, void* workspace, size_t workspace_bytes,
+                     void* stream) {
+    if (int rc = check_layout(lay)) return rc;
+    RPGP_REQUIRE(rpgp_mvm_sym_supported(lay, t), "mvm_sym: needs K == 1, J <= 32 and t <= 16 (got K=%d, chunks=%d, t=%d)", lay->K, lay->nchunks, t);
+    RPGP_REQUIRE(n >= 1 && ldo >= t, "mvm_sym: n=%lld ldo=%d", (long long)n, ldo);
+    RPGP_REQUIRE(zp && neg_log2c && Vp16 && out, "mvm_sym: NULL pointer");
+    RPGP_REQUIRE(aligned16(zp) && aligned16(Vp16), "mvm_sym: operands must be 16-byte aligned");
+    const int nblocks = (int)((n + 127) / 128);
+    RPGP_REQUIRE(0 <= row_block_begin && row_block_begin <= row_block_end && row_block_end <= nblocks,
+                 "mvm_sym: row block range [%d, %d) outside [0, %d]", row_block_begin, row_block_end, nblocks);
+    return launch_sym_tc(zp, n, lay->CP, neg_log2c, Vp16, 16, t, out, ldo, row_block_begin, row_block_end, 1, workspace,
+                         workspace_bytes, (cudaStream_t)stream);
 }
 
 size_t rpgp_quad_workspace_bytes(int64_t m, int64_t n, const rpgp_layout* lay, int t) {

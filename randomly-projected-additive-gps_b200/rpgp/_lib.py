@@ -43,6 +43,10 @@ SIGNATURES = {
     "rpgp_mvm_workspace_bytes": (c_size_t, [c_int64, c_int64, POINTER(Layout), c_int]),
     "rpgp_mvm_fwd_f32": (c_int, [c_void_p, c_int64, c_int64, c_void_p, c_int64, c_int64, POINTER(Layout), c_void_p,
                                  c_void_p, c_int, c_void_p, c_int, c_void_p, c_size_t, c_void_p]),
+    "rpgp_mvm_sym_workspace_bytes": (c_size_t, [c_int64, POINTER(Layout)]),
+    "rpgp_mvm_sym_supported": (c_int, [POINTER(Layout), c_int]),
+    "rpgp_mvm_sym_f32": (c_int, [c_void_p, c_int64, POINTER(Layout), c_void_p, c_void_p, c_int, c_void_p, c_int, c_int,
+                                 c_int, c_void_p, c_size_t, c_void_p]),
     "rpgp_quad_workspace_bytes": (c_size_t, [c_int64, c_int64, POINTER(Layout), c_int]),
     "rpgp_quad_bwd_f32": (c_int, [c_void_p, c_int64, c_int64, c_void_p, c_int64, c_int64, POINTER(Layout), c_void_p,
                                   c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_int, c_void_p, c_void_p, c_void_p,
@@ -229,6 +233,38 @@ def mvm_fwd(z1p, z2p, lay, nlc, V, row_range=None, events=None):
             _check(lib.rpgp_mvm_fwd_f32(z1_ptr, m, m_full * lay.CP, _ptr(z2p), n, n * lay.CP, ctypes.byref(lay),
                                         _ptr(nlc), _ptr(Vp), tc, _ptr(o), out.stride(0), _ptr(ws), ws_bytes, st),
                    "rpgp_mvm_fwd_f32")
+        if events is not None:
+            events[1].record()
+    return out
+
+
+def mvm_sym_supported(lay, t):
+    return bool(load().rpgp_mvm_sym_supported(ctypes.byref(lay), int(t)))
+
+
+def mvm_sym(zp, lay, nlc, V, block_range=None, events=None):
+    """Symmetric K(Z,Z) @ V on the tensor cores (every kernel value evaluated once).  block_range=(b0, b1) restricts to the
+    unique block pairs owned by 128-row blocks [b0, b1): the result then holds partial sums for ALL rows (all-reduce it)."""
+    require_cuda(zp, nlc, V)
+    assert zp.dtype == torch.float32 and zp.is_contiguous() and zp.shape[0] == 1
+    lib = load()
+    n, t = zp.shape[1], V.shape[1]
+    assert V.shape[0] == n
+    nblocks = (n + 127) // 128
+    b0, b1 = (0, nblocks) if block_range is None else block_range
+    out = torch.empty((n, t), dtype=torch.float32, device=V.device)
+    with torch.cuda.device(V.device):
+        st = _stream(V.device)
+        for t0 in range(0, t, 16):
+            tc = min(16, t - t0)
+            Vp = pad_rhs(V[:, t0:t0 + tc].float(), 16)
+            nbytes = lib.rpgp_mvm_sym_workspace_bytes(n, ctypes.byref(lay))
+            ws, ws_bytes = _workspace(V.device, nbytes)
+            o = out[:, t0:t0 + tc]
+            if events is not None and t0 == 0:
+                events[0].record()
+            _check(lib.rpgp_mvm_sym_f32(_ptr(zp), n, ctypes.byref(lay), _ptr(nlc), _ptr(Vp), tc, _ptr(o), out.stride(0),
+                                        int(b0), int(b1), _ptr(ws), ws_bytes, st), "rpgp_mvm_sym_f32")
         if events is not None:
             events[1].record()
     return out

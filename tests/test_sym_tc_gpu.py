@@ -1,0 +1,64 @@
+"""GPU parity of the symmetric tensor-core forward (rpgp_mvm_sym_f32: tcgen05, 3xTF32 split, every kernel value used for
+both out[i] and out[i']) against the FP64 oracle and against the SIMT forward kernel; tolerance 1e-5 relative."""
+import numpy as np
+import pytest
+import torch
+
+from oracle import rpgp_oracle as orc
+from rpgp import _lib
+
+pytestmark = pytest.mark.gpu
+DEV = torch.device("cuda:0")
+
+
+def rel(a, b):
+    a, b = np.asarray(a, np.float64), np.asarray(b, np.float64)
+    return np.linalg.norm(a - b) / max(np.linalg.norm(b), 1e-300)
+
+
+def setup(n, J, t, seed, spread=1.0):
+    rng = np.random.RandomState(seed)
+    Z = (rng.randn(n, J) * spread).astype(np.float32)
+    c = (rng.rand(J) + 0.1).astype(np.float32)
+    V = rng.randn(n, t).astype(np.float32)
+    lay = _lib.plan_layout(J, 1)
+    zp = _lib.pack_coords(torch.from_numpy(Z).to(DEV), lay)
+    nlc = _lib.pack_log2c(torch.from_numpy(c).to(DEV), lay)
+    return Z, c, V, lay, zp, nlc
+
+
+@pytest.mark.parametrize("n,J,t", [(50, 20, 11), (128, 20, 11), (129, 20, 3), (300, 20, 11), (777, 20, 1), (1000, 20, 16),
+                                   (1024, 26, 16), (2500, 20, 11), (640, 7, 5), (900, 32, 11), (385, 3, 2)])
+def test_sym_matches_oracle(n, J, t):
+    Z, c, V, lay, zp, nlc = setup(n, J, t, seed=n + J)
+    assert _lib.mvm_sym_supported(lay, t)
+    got = _lib.mvm_sym(zp, lay, nlc, torch.from_numpy(V).to(DEV)).cpu().numpy()
+    ref = orc.kmv(Z, Z, c, J, 1, V)
+    assert np.isfinite(got).all()
+    assert rel(got, ref) < 1e-5, rel(got, ref)
+
+
+def test_sym_agrees_with_simt_forward_and_wide_spread():
+    Z, c, V, lay, zp, nlc = setup(3000, 20, 11, seed=1, spread=9.5)
+    Vd = torch.from_numpy(V).to(DEV)
+    a = _lib.mvm_sym(zp, lay, nlc, Vd).cpu().numpy()
+    b = _lib.mvm_fwd(zp, zp, lay, nlc, Vd).cpu().numpy()
+    assert rel(a, b) < 2e-6, rel(a, b)
+    assert rel(a, orc.kmv(Z, Z, c, 20, 1, V)) < 1e-5
+
+
+def test_sym_block_ranges_sum_to_full():
+    Z, c, V, lay, zp, nlc = setup(1500, 20, 11, seed=2)
+    Vd = torch.from_numpy(V).to(DEV)
+    full = _lib.mvm_sym(zp, lay, nlc, Vd).cpu().numpy().astype(np.float64)
+    nb = (1500 + 127) // 128
+    parts = sum(_lib.mvm_sym(zp, lay, nlc, Vd, block_range=(b0, b1)).cpu().numpy().astype(np.float64)
+                for b0, b1 in [(0, 4), (4, 9), (9, nb)])
+    assert rel(parts, full) < 2e-6
+    torch.cuda.synchronize()
+
+
+def test_sym_unsupported_shapes_are_reported():
+    assert not _lib.mvm_sym_supported(_lib.plan_layout(20, 5), 11)
+    assert not _lib.mvm_sym_supported(_lib.plan_layout(90, 1), 11)
+    assert not _lib.mvm_sym_supported(_lib.plan_layout(20, 1), 17)

@@ -48,3 +48,25 @@ def run_bwd(n, J, t, spread, reps=3):
 run_bwd(100_000, 20, 11, 1.0)
 run_bwd(100_000, 20, 11, 4.5)
 run_bwd(100_000, 26, 16, 1.4)
+
+def run_sym(n, J, t, spread, reps=3):
+    lay = _lib.plan_layout(J, 1)
+    g = torch.Generator(device=dev); g.manual_seed(0)
+    Z = torch.randn(n, J, device=dev, generator=g) * spread
+    zp = _lib.pack_coords(Z, lay)
+    nlc = _lib.pack_log2c(torch.full((J,), 0.03, device=dev), lay)
+    V = torch.randn(n, t, device=dev, generator=g)
+    for _ in range(2): _lib.mvm_sym(zp, lay, nlc, V)
+    torch.cuda.synchronize()
+    e0 = torch.cuda.Event(enable_timing=True); e1 = torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(reps): _lib.mvm_sym(zp, lay, nlc, V)
+    e1.record(); torch.cuda.synchronize()
+    ms = e0.elapsed_time(e1) / reps
+    pe = n * n * J / (ms * 1e-3)
+    print(f"SYM-TC n={n} J={J} t={t} spread={spread}: {ms:.3f} ms  {pe/1e12:.3f} T pair-evals/s  ({pe/4.65e12*100:.1f}% of the MUFU roof of the non-symmetric algorithm)", flush=True)
+import os
+if os.environ.get("RPGP_SYM_BENCH", "1") == "1":
+    run_sym(100_000, 20, 11, 1.0)
+    run_sym(100_000, 20, 11, 4.5)
+    run_sym(200_000, 20, 11, 4.5, reps=2)
