@@ -9,4 +9,7 @@ size_t sym_workspace_bytes(long long n);
 // accumulators in the workspace.
 int launch_sym_tc(const float* zp, long long n, int CP, const float* nlc, const float* V, int ldv, int t, float* out, int ldo,
                   int rb_begin, int rb_end, int finalize, void* workspace, size_t workspace_bytes, cudaStream_t st);
+// warp-specialised variant (sym_tc3.cu): row side in registers, column side on the tensor cores issued by dedicated warps
+int launch_sym_tc3(const float* zp, long long n, int CP, const float* nlc, const float* V16, int t, float* out, int ldo,
+                   int rb_begin, int rb_end, void* workspace, size_t workspace_bytes, cudaStream_t st);
 }  // namespace rpgp
