@@ -206,6 +206,11 @@ def run_ours(args, w):
     del Xd
     nlc = _lib.pack_log2c(c.to(dev), lay)
 
+    use_sym = (not args.no_sym) and _lib.mvm_sym_supported(lay, t) and lay.nchunks == 1
+    nblocks128 = (n + 127) // 128
+    sper = (nblocks128 + world - 1) // world
+    sb0, sb1 = min(nblocks128, rank * sper), min(nblocks128, (rank + 1) * sper)
+
     # CG state (replicated on every rank, updated identically): solve K^ x = V
     x = torch.zeros_like(Vd)
     r = Vd.clone()
@@ -222,14 +227,20 @@ def run_ours(args, w):
             kernel_events.append(ev)
         else:
             ev = None
-        Kp_blk = _lib.mvm_fwd(zp, zp, lay, nlc, p, row_range=(r0, r1), events=ev)
-        if world > 1:
-            if Kp_blk.shape[0] < blk:
-                Kp_blk = torch.cat([Kp_blk, Kp_blk.new_zeros((blk - Kp_blk.shape[0], t))])
-            dist.all_gather_into_tensor(Kp_full, Kp_blk.contiguous())
-            Kp = Kp_full[:n]
+        if use_sym:
+            # symmetric tensor-core kernel: this rank's share of the unique 128-row block pairs, partial sums for all rows
+            Kp = _lib.mvm_sym(zp, lay, nlc, p, block_range=(sb0, sb1), events=ev)
+            if world > 1:
+                dist.all_reduce(Kp, op=dist.ReduceOp.SUM)
         else:
-            Kp = Kp_blk
+            Kp_blk = _lib.mvm_fwd(zp, zp, lay, nlc, p, row_range=(r0, r1), events=ev)
+            if world > 1:
+                if Kp_blk.shape[0] < blk:
+                    Kp_blk = torch.cat([Kp_blk, Kp_blk.new_zeros((blk - Kp_blk.shape[0], t))])
+                dist.all_gather_into_tensor(Kp_full, Kp_blk.contiguous())
+                Kp = Kp_full[:n]
+            else:
+                Kp = Kp_blk
         Kp = Kp + noise * p
         alpha = rz / (p * Kp).sum(0).clamp_min(1e-30)
         x.add_(p * alpha)
@@ -320,9 +331,13 @@ def run_ours(args, w):
         "bound": "mufu", "achieved": ach / 1e12, "peak": mufu_peak / 1e12, "unit": "Tex2/s", "frac": ach / mufu_peak,
         "peak_source": "measured live: rpgp_measure_peaks mufu_ex2 %.2f/clk/SM x %d SMs x %.0f MHz"
                        % (peaks["mufu_ex2"]["mufu_per_clk_sm"], sms, peaks["mufu_ex2"]["mhz"]),
-        "kernel": "mvm_fwd_kernel<CP=%d,TP=%d,KP=%d,G=%d>" % (lay.CP, _lib.padded_rhs(lay, min(t, 16), False), lay.KP, lay.G),
+        "kernel": ("mvm_sym_tc3_kernel<CP=%d> (symmetric: each kernel value evaluated once, column side on tcgen05)" % lay.CP) if use_sym
+                  else "mvm_fwd_kernel<CP=%d,TP=%d,KP=%d,G=%d>" % (lay.CP, _lib.padded_rhs(lay, min(t, 16), False), lay.KP, lay.G),
+        "note": "achieved counts the ALGORITHMIC exponentials of SURVEY 8(d) (m*n*J per product); the kernel evaluates fewer on the "
+                "XU pipe (symmetry halves them, ~20% more go to an FMA-pipe polynomial), so frac can exceed 1" if use_sym else
+                "achieved counts the algorithmic exponentials m*n*J; ~20% of them are evaluated by an FMA-pipe polynomial, so frac can exceed 1",
         "kernel_ms": kernel_ms, "kernel_share_of_step": kernel_ms / ms_per_step,
-        "algorithmic_ex2_per_launch": ex2_alg, "issued_ex2_per_launch": float(m_rows) * n * groups,
+        "algorithmic_ex2_per_launch": ex2_alg, "issued_ex2_per_launch": (float(n) * n * groups / 2 / world) if use_sym else float(m_rows) * n * groups,
         "fp32_frac": (fp32_alg / (kernel_ms * 1e-3)) / fp32_peak, "fp32_peak_Tlaneops": fp32_peak / 1e12,
         "traffic": traffic,
         "hbm": {"algorithmic_bytes_per_launch": alg_bytes, "achieved_GBps": alg_bytes / (kernel_ms * 1e-3) / 1e9,
@@ -420,6 +435,7 @@ def main():
     ap.add_argument("--e2e-steps", type=int, default=2)
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-sym", action="store_true", help="use the SIMT forward kernel instead of the symmetric tensor-core kernel")
     ap.add_argument("--mode", default="cg", choices=["cg", "mll"], help="cg: one CG iteration per step (headline); mll: full MLL+gradient step")
     ap.add_argument("--cg-tol", type=float, default=0.002)
     args = ap.parse_args()

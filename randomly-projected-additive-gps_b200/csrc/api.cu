@@ -313,7 +313,9 @@ int rpgp_kmv_host_f32(const float* X1, int64_t m, const float* X2, int64_t n, in
     rpgp_layout lay;
     if (int rc = rpgp_plan_layout(J, K, &lay)) return rc;
     const int JK = J * K;
-    const int tmax = rpgp_max_rhs(&lay, 0);
+    // square products of a few thousand rows or more go to the symmetric tensor-core kernel (16 right-hand sides per pass)
+    const bool use_sym = square && m >= 1024 && rpgp_mvm_sym_supported(&lay, std::min(t, 16));
+    const int tmax = use_sym ? 16 : rpgp_max_rhs(&lay, 0);
     const float scale = (float)COORD_SCALE_D;
 
     struct Buffers {
@@ -346,10 +348,10 @@ int rpgp_kmv_host_f32(const float* X1, int64_t m, const float* X2, int64_t n, in
     if (!square && (rc = buf.alloc((void**)&dZ2, (size_t)lay.nchunks * n * lay.CP * 4))) return rc;
     if ((rc = buf.alloc((void**)&dV, (size_t)n * t * 4))) return rc;
     const int tc0 = std::min(t, tmax);
-    const int TP0 = rpgp_padded_rhs(&lay, tc0, 0);
+    const int TP0 = use_sym ? 16 : rpgp_padded_rhs(&lay, tc0, 0);
     if ((rc = buf.alloc((void**)&dVp, (size_t)n * TP0 * 4))) return rc;
     if ((rc = buf.alloc((void**)&dout, (size_t)m * t * 4))) return rc;
-    const size_t ws_bytes = rpgp_mvm_workspace_bytes(m, n, &lay, tc0);
+    const size_t ws_bytes = use_sym ? rpgp_mvm_sym_workspace_bytes(n, &lay) : rpgp_mvm_workspace_bytes(m, n, &lay, tc0);
     if ((rc = buf.alloc(&dws, ws_bytes))) return rc;
 
     RPGP_CUDA_OK(cudaMemcpyAsync(dX1, X1, (size_t)m * d * 4, cudaMemcpyHostToDevice, st));
@@ -366,14 +368,16 @@ int rpgp_kmv_host_f32(const float* X1, int64_t m, const float* X2, int64_t n, in
     const float* z2 = square ? dZ1 : dZ2;
     for (int t0 = 0; t0 < t; t0 += tmax) {
         const int tc = std::min(tmax, t - t0);
-        const int TP = rpgp_padded_rhs(&lay, tc, 0);
+        const int TP = use_sym ? 16 : rpgp_padded_rhs(&lay, tc, 0);
         // pad this block of right-hand sides to [n][TP]
         RPGP_CUDA_OK(cudaMemsetAsync(dVp, 0, (size_t)n * TP * 4, st));
         RPGP_CUDA_OK(cudaMemcpy2DAsync(dVp, (size_t)TP * 4, dV + t0, (size_t)t * 4, (size_t)tc * 4, (size_t)n,
                                        cudaMemcpyDeviceToDevice, st));
-        if ((rc = rpgp_mvm_fwd_f32(dZ1, m, m * lay.CP, z2, n, n * lay.CP, &lay, dnlc, dVp, tc, dout + t0, t, dws,
-                                   ws_bytes, st)))
-            return rc;
+        if (use_sym)
+            rc = rpgp_mvm_sym_f32(dZ1, n, &lay, dnlc, dVp, tc, dout + t0, t, 0, (int)((n + 127) / 128), dws, ws_bytes, st);
+        else
+            rc = rpgp_mvm_fwd_f32(dZ1, m, m * lay.CP, z2, n, n * lay.CP, &lay, dnlc, dVp, tc, dout + t0, t, dws, ws_bytes, st);
+        if (rc) return rc;
     }
     if (square && diag_add != 0.f && (rc = launch_axpy_rows(diag_add, dV, t, m, t, dout, t, st))) return rc;
     RPGP_CUDA_OK(cudaMemcpyAsync(out, dout, (size_t)m * t * 4, cudaMemcpyDeviceToHost, st));

@@ -15,7 +15,18 @@ import torch
 from . import _lib
 from . import dist as rdist
 
+import os
+
 LN2 = 0.6931471805599453
+# symmetric products K(Z,Z).V of at least this many rows go to the tensor-core kernel that evaluates every kernel value once
+# (rpgp_mvm_sym_f32); RPGP_SYM=0 keeps everything on the SIMT forward kernel
+SYM_MIN_ROWS = int(os.environ.get("RPGP_SYM_MIN_ROWS", "1024"))
+SYM_ENABLED = os.environ.get("RPGP_SYM", "1") != "0"
+
+
+def _use_sym(p1, p2, t, row_range):
+    return (SYM_ENABLED and p2 is p1 and row_range is None and p1.n >= SYM_MIN_ROWS and p1.zp.shape[0] == 1
+            and _lib.mvm_sym_supported(p1.lay, min(t, 16)))
 
 
 class Packed:
@@ -74,7 +85,10 @@ def kmv_raw(Z1, Z2, c, J, K, V, packed1=None, packed2=None, nlc=None, row_range=
     p1 = packed1 or Packed(Z1, J, K)
     p2 = packed2 or (p1 if Z2 is Z1 else Packed(Z2, J, K))
     nlc = nlc if nlc is not None else pack_weights(c, p1.lay)
-    return _lib.mvm_fwd(p1.zp, p2.zp, p1.lay, nlc, V.contiguous().float(), row_range=row_range)
+    V = V.contiguous().float()
+    if _use_sym(p1, p2, V.shape[1], row_range):
+        return _lib.mvm_sym(p1.zp, p1.lay, nlc, V)
+    return _lib.mvm_fwd(p1.zp, p2.zp, p1.lay, nlc, V, row_range=row_range)
 
 
 def quad_form_grads(Z1, Z2, c, J, K, L, R, symmetric, packed1=None, packed2=None, nlc=None, row_range=None):
@@ -205,5 +219,16 @@ def kmv_partitioned(Z, c, J, K, V, packed=None, nlc=None):
     part = rdist.partition(Z.shape[0])
     if part.world == 1:
         return kmv_raw(Z, Z, c, J, K, V, packed1=packed, packed2=packed, nlc=nlc)
+    if Z.dtype == torch.float32:
+        p = packed or Packed(Z, J, K)
+        if _use_sym(p, p, V.shape[1], None):
+            # symmetric tensor-core kernel: rank r owns the unique block pairs of its share of the 128-row blocks and
+            # produces partial sums for ALL rows -> the exchange is an all-reduce (sum) instead of an all-gather
+            nblocks = (p.n + 127) // 128
+            per = (nblocks + part.world - 1) // part.world
+            b0, b1 = min(nblocks, part.rank * per), min(nblocks, (part.rank + 1) * per)
+            w = nlc if nlc is not None else pack_weights(_expand_c(c, J, Z), p.lay)
+            out = _lib.mvm_sym(p.zp, p.lay, w, V.contiguous().float(), block_range=(b0, b1))
+            return rdist.all_reduce_sum(out)
     blk = kmv_raw(Z, Z, c, J, K, V, packed1=packed, packed2=packed, nlc=nlc, row_range=(part.r0, part.r1))
     return rdist.all_gather_rows(blk, part)
