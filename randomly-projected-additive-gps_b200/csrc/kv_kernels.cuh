@@ -130,10 +130,13 @@ __device__ __forceinline__ float pair_kernel_value(const RowCoords<CP, KP, G>& r
                 unpack2(u, ul, uh);
                 e = pack2(ex2_ftz(-ul), ex2_ftz(-uh));
             }
-            if (q & 1) s1 = add2(s1, e); else s0 = add2(s0, e);
+            if (q == 0) s0 = e;                          // two partial sums; no add for their first terms
+            else if (q == 1) s1 = e;
+            else if (q & 1) s1 = add2(s1, e);
+            else s0 = add2(s0, e);
         }
         float lo, hi;
-        unpack2(add2(s0, s1), lo, hi);
+        if constexpr (CP / 2 >= 2) unpack2(add2(s0, s1), lo, hi); else unpack2(s0, lo, hi);
         return lo + hi;
     } else {
         float s = 0.f;

@@ -15,6 +15,8 @@
 // CTA = 256 threads: warpgroup 0 = 4 arithmetic warps (thread = row, 128 rows, 200 registers via setmaxnreg),
 // warpgroup 1 = warp 4/5 MMA issue + column-side epilogue (FP64 atomics), warp 6 TMA producer (z and V tiles), 56 registers.
 #include <algorithm>
+#include <cstdlib>
+#include <type_traits>
 
 #include "aux_kernels.cuh"
 #include "kv_kernels.cuh"
@@ -27,6 +29,10 @@ namespace {
 constexpr int T3_ROWS = 128;     // rows per CTA
 constexpr int T3_BN = 32;        // columns per tile
 constexpr int T3_N = 16;         // padded right-hand sides
+#ifndef T3_QUNROLL
+#define T3_QUNROLL 1
+#endif
+constexpr int T3_QU = T3_QUNROLL;   // unroll factor of the 4-column groups inside a tile
 
 // shared-memory map (bytes from a 1024-aligned base)
 constexpr uint32_t T3_SC = 0;                  // S^T operand: buffer b at b*32768: hi [128 rows][128 B], lo 16384 B later
@@ -68,6 +74,21 @@ __device__ __forceinline__ void umma3_commit(uint64_t* bar) {
 }
 __device__ __forceinline__ void mbar_arrive(uint64_t* bar) {
     asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
+// helper warps poll with a back-off so that their spinning does not take issue slots from the arithmetic warps
+__device__ __forceinline__ void mbar_wait_sleep(uint64_t* bar, uint32_t parity) {
+    uint32_t done = 0;
+    while (true) {
+        asm volatile(
+            "{\n\t.reg .pred p;\n\t"
+            "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+            "selp.u32 %0, 1, 0, p;\n\t}\n"
+            : "=r"(done)
+            : "r"(smem_u32(bar)), "r"(parity)
+            : "memory");
+        if (done) break;
+        __nanosleep(128);
+    }
 }
 __device__ __forceinline__ void tc3_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
 __device__ __forceinline__ void tc3_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
@@ -111,7 +132,7 @@ struct TileIter {
 
 }  // namespace
 
-template <int CP, int NP2>
+template <int CP, int NP2, int TP>
 __global__ void __launch_bounds__(256, 2) mvm_sym_tc3_kernel(const Sym3Args a) {
     extern __shared__ unsigned char smem_raw[];
     const uint32_t base = (smem_u32(smem_raw) + 1023u) & ~1023u;
@@ -169,9 +190,9 @@ __global__ void __launch_bounds__(256, 2) mvm_sym_tc3_kernel(const Sym3Args a) {
                 *reinterpret_cast<float*>(sm + T3_BCL + off) = v - h;
             }
         }
-        f32x2 acc[T3_N / 2], comp[T3_N / 2];
+        f32x2 acc[TP / 2], comp[TP / 2];   // TP = right-hand sides rounded up to 4 (row side only; the MMA N stays 16)
 #pragma unroll
-        for (int q = 0; q < T3_N / 2; ++q) { acc[q] = 0ull; comp[q] = 0ull; }
+        for (int q = 0; q < TP / 2; ++q) { acc[q] = 0ull; comp[q] = 0ull; }
 
         int j = 0, jc = 0;
         for (int t = it.next_live(0); t < it.ntiles; t = it.next_live(t + 1), ++j) {
@@ -185,36 +206,40 @@ __global__ void __launch_bounds__(256, 2) mvm_sym_tc3_kernel(const Sym3Args a) {
             const float* zt = reinterpret_cast<const float*>(sm + T3_Z) + (size_t)s * T3_BN * CP;
             const float* vt = reinterpret_cast<const float*>(sm + T3_V) + (size_t)s * T3_BN * T3_N;
             unsigned char* sc = sm + T3_SC + (uint32_t)bc * 32768u;
-            f32x2 lo[T3_N / 2];
+            f32x2 lo[TP / 2];
 #pragma unroll
-            for (int q = 0; q < T3_N / 2; ++q) lo[q] = 0ull;
-#pragma unroll 1
-            for (int q = 0; q < T3_BN / 4; ++q) {
-                float sv[4];
+            for (int q = 0; q < TP / 2; ++q) lo[q] = 0ull;
+            auto tile_body = [&](auto full_tile) {
+                constexpr bool FULL = decltype(full_tile)::value;
+#pragma unroll T3_QU
+                for (int q = 0; q < T3_BN / 4; ++q) {
+                    float sv[4];
 #pragma unroll
-                for (int e = 0; e < 4; ++e) {
-                    const int c = 4 * q + e;
-                    const float val = pair_kernel_value<CP, 1, CP, NP2>(r, zt + c * CP);
-                    sv[e] = (c < cols) ? val : 0.f;      // columns behind a partial tile hold stale bytes
-                    const f32x2 ss = pack2(sv[e], sv[e]);
+                    for (int e = 0; e < 4; ++e) {
+                        const int c = 4 * q + e;
+                        const float val = pair_kernel_value<CP, 1, CP, NP2>(r, zt + c * CP);
+                        sv[e] = (FULL || c < cols) ? val : 0.f;      // columns behind a partial tile hold stale bytes
+                        const f32x2 ss = pack2(sv[e], sv[e]);
 #pragma unroll
-                    for (int k = 0; k < T3_N / 4; ++k) {   // row side: out[i,:] += k(i,i') V[i',:]
-                        const ulonglong2 p = *reinterpret_cast<const ulonglong2*>(vt + c * T3_N + 4 * k);
-                        lo[2 * k] = fma2(ss, p.x, lo[2 * k]);
-                        lo[2 * k + 1] = fma2(ss, p.y, lo[2 * k + 1]);
+                        for (int k = 0; k < TP / 4; ++k) {   // row side: out[i,:] += k(i,i') V[i',:]
+                            const ulonglong2 p = *reinterpret_cast<const ulonglong2*>(vt + c * T3_N + 4 * k);
+                            lo[2 * k] = fma2(ss, p.x, lo[2 * k]);
+                            lo[2 * k + 1] = fma2(ss, p.y, lo[2 * k + 1]);
+                        }
+                    }
+                    if (!diag) {   // column side operand: split, SWIZZLE_128B_BASE32B (32-byte chunks ^ row % 4), row-local stores
+                        float4 h, l;
+                        h.x = tf32_hi3(sv[0]); h.y = tf32_hi3(sv[1]); h.z = tf32_hi3(sv[2]); h.w = tf32_hi3(sv[3]);
+                        l.x = sv[0] - h.x; l.y = sv[1] - h.y; l.z = sv[2] - h.z; l.w = sv[3] - h.w;
+                        const uint32_t off = (uint32_t)tid * 128u + (((((uint32_t)q >> 1) ^ ((uint32_t)tid & 3u)) << 5) | (((uint32_t)q & 1u) << 4));
+                        *reinterpret_cast<float4*>(sc + off) = h;
+                        *reinterpret_cast<float4*>(sc + 16384u + off) = l;
                     }
                 }
-                if (!diag) {   // column side operand: split, SWIZZLE_128B_BASE32B (32-byte chunks ^ row % 4), row-local stores
-                    float4 h, l;
-                    h.x = tf32_hi3(sv[0]); h.y = tf32_hi3(sv[1]); h.z = tf32_hi3(sv[2]); h.w = tf32_hi3(sv[3]);
-                    l.x = sv[0] - h.x; l.y = sv[1] - h.y; l.z = sv[2] - h.z; l.w = sv[3] - h.w;
-                    const uint32_t off = (uint32_t)tid * 128u + (((((uint32_t)q >> 1) ^ ((uint32_t)tid & 3u)) << 5) | (((uint32_t)q & 1u) << 4));
-                    *reinterpret_cast<float4*>(sc + off) = h;
-                    *reinterpret_cast<float4*>(sc + 16384u + off) = l;
-                }
-            }
+            };
+            if (cols == T3_BN) tile_body(std::true_type{}); else tile_body(std::false_type{});
 #pragma unroll
-            for (int q = 0; q < T3_N / 2; ++q) {   // Kahan-compensated fold of the tile sum
+            for (int q = 0; q < TP / 2; ++q) {   // Kahan-compensated fold of the tile sum
                 const f32x2 y = sub2(lo[q], comp[q]);
                 const f32x2 tsum = add2(acc[q], y);
                 comp[q] = sub2(sub2(tsum, acc[q]), y);
@@ -233,7 +258,7 @@ __global__ void __launch_bounds__(256, 2) mvm_sym_tc3_kernel(const Sym3Args a) {
         if (valid && j > 0) {
             double* dst = a.acc + row * T3_N;
 #pragma unroll
-            for (int q = 0; q < T3_N / 2; ++q) {
+            for (int q = 0; q < TP / 2; ++q) {
                 float x, y;
                 unpack2(acc[q], x, y);
                 atomicAdd(dst + 2 * q, (double)x);
@@ -248,7 +273,7 @@ __global__ void __launch_bounds__(256, 2) mvm_sym_tc3_kernel(const Sym3Args a) {
                 int j = 0;
                 for (int t = it.next_live(0); t < it.ntiles; t = it.next_live(t + 1), ++j) {
                     const int s = j & 1;
-                    if (j >= 2) mbar_wait(&bars[B_ZEMPTY + s], (uint32_t)(((j >> 1) - 1) & 1));
+                    if (j >= 2) mbar_wait_sleep(&bars[B_ZEMPTY + s], (uint32_t)(((j >> 1) - 1) & 1));
                     const long long c0 = it.col0(t);
                     const uint32_t cols = (uint32_t)min((long long)T3_BN, a.n - c0);
                     mbar_expect_tx(&bars[B_ZFULL + s], cols * (CP + T3_N) * (uint32_t)sizeof(float));
@@ -265,7 +290,7 @@ __global__ void __launch_bounds__(256, 2) mvm_sym_tc3_kernel(const Sym3Args a) {
             long long prev_c0 = -1;
             auto epilogue = [&](int pjc, long long pc0) {
                 const int pb = pjc & 1;
-                mbar_wait(&bars[B_TDONE + pb], (uint32_t)((pjc >> 1) & 1));
+                mbar_wait_sleep(&bars[B_TDONE + pb], (uint32_t)((pjc >> 1) & 1));
                 tc3_fence_after();
                 float d0[16], d1[16];
                 const uint32_t lane_base = (uint32_t)(h * 32) << 16;
@@ -283,13 +308,13 @@ __global__ void __launch_bounds__(256, 2) mvm_sym_tc3_kernel(const Sym3Args a) {
             for (int t = it.next_live(0); t < it.ntiles; t = it.next_live(t + 1)) {
                 if (it.diag(t)) continue;
                 const int bc = jc & 1;
-                if (jc >= 2) mbar_wait(&bars[B_EREAD + bc], (uint32_t)(((jc >> 1) - 1) & 1));   // both issuers have read D2 of tile jc-2
+                if (jc >= 2) mbar_wait_sleep(&bars[B_EREAD + bc], (uint32_t)(((jc >> 1) - 1) & 1));   // both issuers have read D2 of tile jc-2
                 const uint32_t d2 = tmem + 32u * bc + 16u * h;
                 const uint64_t dA_h = smem_desc3(base + T3_SC + (uint32_t)bc * 32768u, 16384, 512, LAYOUT_SW128_BASE32B);
                 const uint64_t dA_l = smem_desc3(base + T3_SC + (uint32_t)bc * 32768u + 16384u, 16384, 512, LAYOUT_SW128_BASE32B);
 #pragma unroll 1
                 for (int sw = 2 * h; sw < 2 * h + 2; ++sw) {
-                    mbar_wait(&bars[B_SFULL + sw * 2 + bc], (uint32_t)((jc >> 1) & 1));
+                    mbar_wait_sleep(&bars[B_SFULL + sw * 2 + bc], (uint32_t)((jc >> 1) & 1));
                     tc3_fence_after();
                     if (lane == 0) {
 #pragma unroll
@@ -320,9 +345,9 @@ __global__ void __launch_bounds__(256, 2) mvm_sym_tc3_kernel(const Sym3Args a) {
     }
 }
 
-template <int CP, int NP2>
+template <int CP, int NP2, int TP>
 static int run_sym3(const Sym3Args& a, dim3 grid, cudaStream_t st) {
-    auto kernel = mvm_sym_tc3_kernel<CP, NP2>;
+    auto kernel = mvm_sym_tc3_kernel<CP, NP2, TP>;
     cudaError_t e = cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)T3_SMEM_BYTES);
     if (e != cudaSuccess) return cuda_fail(e, "cudaFuncSetAttribute(mvm_sym_tc3_kernel)");
     kernel<<<grid, 256, T3_SMEM_BYTES, st>>>(a);
@@ -358,18 +383,22 @@ int launch_sym_tc3(const float* zp, long long n, int CP, const float* nlc, const
         want = std::max<long long>(1, std::min<long long>(want, a.half));
         a.nsplits = (int)want;
         dim3 grid((unsigned)nrb, (unsigned)a.nsplits, 1);
+        // polynomial-exp2 pairs: this kernel is bound by instruction issue (an FFMA2 takes two issue cycles), so fewer pairs
+        // go to the FMA pipe than in the forward kernel; RPGP_SYM_POLY_PAIRS overrides (tools sweep)
+        static const int np_env = [] { const char* e = getenv("RPGP_SYM_POLY_PAIRS"); return e ? atoi(e) : -1; }();
+        const int tp = t <= 4 ? 4 : (t <= 8 ? 8 : (t <= 12 ? 12 : 16));
         int rc = ERR_UNSUPPORTED;
-        switch (CP) {
-            case 4: rc = run_sym3<4, 0>(a, grid, st); break;
-            case 8: rc = run_sym3<8, 1>(a, grid, st); break;
-            case 12: rc = run_sym3<12, 1>(a, grid, st); break;
-            case 16: rc = run_sym3<16, 2>(a, grid, st); break;
-            case 20: rc = run_sym3<20, 2>(a, grid, st); break;
-            case 24: rc = run_sym3<24, 2>(a, grid, st); break;
-            case 28: rc = run_sym3<28, 3>(a, grid, st); break;
-            case 32: rc = run_sym3<32, 3>(a, grid, st); break;
-            default: set_error("mvm_sym: unsupported CP=%d", CP);
+#define RPGP_SYM3_CASE(CPv, NPv)                                                                              \
+        if (CP == CPv && np == NPv) {                                                                         \
+            rc = tp == 4 ? run_sym3<CPv, NPv, 4>(a, grid, st) : tp == 8 ? run_sym3<CPv, NPv, 8>(a, grid, st)    \
+                 : tp == 12 ? run_sym3<CPv, NPv, 12>(a, grid, st) : run_sym3<CPv, NPv, 16>(a, grid, st);       \
         }
+        const int np = np_env >= 0 ? np_env : (CP >= 20 ? 2 : (CP >= 16 ? 1 : 0));
+        RPGP_SYM3_CASE(4, 0) RPGP_SYM3_CASE(8, 0) RPGP_SYM3_CASE(12, 0) RPGP_SYM3_CASE(16, 0) RPGP_SYM3_CASE(16, 1)
+        RPGP_SYM3_CASE(20, 0) RPGP_SYM3_CASE(20, 1) RPGP_SYM3_CASE(20, 2) RPGP_SYM3_CASE(24, 0) RPGP_SYM3_CASE(24, 1)
+        RPGP_SYM3_CASE(28, 0) RPGP_SYM3_CASE(28, 1) RPGP_SYM3_CASE(32, 0) RPGP_SYM3_CASE(32, 1) RPGP_SYM3_CASE(32, 2)
+#undef RPGP_SYM3_CASE
+        if (rc == ERR_UNSUPPORTED) set_error("mvm_sym: no kernel for CP=%d poly pairs=%d", CP, np);
         if (rc) return rc;
     }
     const long long total = n * t;
