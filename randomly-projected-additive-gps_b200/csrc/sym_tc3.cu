@@ -379,7 +379,9 @@ int launch_sym_tc3(const float* zp, long long n, int CP, const float* nlc, const
     a.rb_begin = rb_begin;
     const int nrb = rb_end - rb_begin;
     if (nrb > 0) {
+        static const int splits_env = [] { const char* e = getenv("RPGP_SYM_SPLITS"); return e ? atoi(e) : 0; }();
         long long want = (148LL * 2 * 16 + nrb - 1) / nrb;
+        if (splits_env > 0) want = splits_env;
         want = std::max<long long>(1, std::min<long long>(want, a.half));
         a.nsplits = (int)want;
         dim3 grid((unsigned)nrb, (unsigned)a.nsplits, 1);
