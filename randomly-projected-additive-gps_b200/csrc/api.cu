@@ -212,11 +212,6 @@ int rpgp_mvm_sym_f32(const float* zp, int64_t n, const rpgp_layout* lay, const f
     const int nblocks = (int)((n + 127) / 128);
     RPGP_REQUIRE(0 <= row_block_begin && row_block_begin <= row_block_end && row_block_end <= nblocks,
                  "mvm_sym: row block range [%d, %d) outside [0, %d]", row_block_begin, row_block_end, nblocks);
-    // RPGP_SYM_IMPL=1 selects the first implementation (both products on the tensor core, one issuing thread)
-    static const int impl = [] { const char* e = getenv("RPGP_SYM_IMPL"); return e ? atoi(e) : 3; }();
-    if (impl == 1)
-        return launch_sym_tc(zp, n, lay->CP, neg_log2c, Vp16, 16, t, out, ldo, row_block_begin, row_block_end, 1, workspace,
-                             workspace_bytes, (cudaStream_t)stream);
     return launch_sym_tc3(zp, n, lay->CP, neg_log2c, Vp16, t, out, ldo, row_block_begin, row_block_end, workspace,
                           workspace_bytes, (cudaStream_t)stream);
 }

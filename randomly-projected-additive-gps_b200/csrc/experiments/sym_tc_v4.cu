@@ -1,0 +1,444 @@
+// sym_tc4.cu -- symmetric K(Z,Z).V, warp-specialised, TWO THREADS PER ROW: every kernel value is computed ONCE by the arithmetic warps, which also
+// apply it to their own rows (row side, packed FFMA2 exactly as in the forward kernel); the transposed use
+//     out[i',:] += sum_i k(i,i') V[i,:]                                   (column side)
+// is a reduction ACROSS the row-owning threads and runs on the tensor cores as S^T . V_I  (tcgen05.mma kind::tf32,
+// 3xTF32 split for FP32 accuracy, accumulators in TMEM).
+//
+// What the microbenchmarks dictated (profiles/umma_microbench_r01.txt):
+//   * an MN-major tf32 operand must be in the SWIZZLE_128B_BASE32B layout -> S is written in that layout, row-locally;
+//   * a UTCHMMA blocks its issuing WARP ~80-150 clk and a small MMA costs that much whatever N is -> the MMAs are issued by
+//     dedicated warps (4 and 5), never by the arithmetic warps, and only the column side (which cannot be done in
+//     registers) goes to the tensor core;
+//   * column-side k-steps are 8 ROWS, i.e. rows of one arithmetic warp -> all hand-offs are warp-local mbarriers; there is no
+//     CTA-wide barrier in the steady state and S is double buffered so the arithmetic never waits for the tensor core.
+//
+// Difference to sym_tc3.cu: a row is shared by the two lanes l and l+16 of a warp -- each evaluates half of the projections and
+// half of the right-hand sides, the two partial kernel sums are exchanged with one SHFL -- so an arithmetic thread needs ~100
+// registers instead of ~165 and the SM holds 16 arithmetic warps instead of 8 (the 8-warp version is latency-bound:
+// profiles/ncu_r01_sym_cfg2_summary.md).
+// CTA = 384 threads: warpgroups 0,1 = 8 arithmetic warps (16 rows each, 128 rows, 96 registers via setmaxnreg),
+// warpgroup 2 = warp 8/9 MMA issue + column-side epilogue (FP64 atomics), warp 10 TMA producer (z and V tiles), 48 registers.
+#include <algorithm>
+#include <cstdlib>
+#include <type_traits>
+
+#include "aux_kernels.cuh"
+#include "kv_kernels.cuh"
+#include "sym_tc.cuh"
+
+namespace rpgp {
+
+namespace {
+
+constexpr int T4_ROWS = 128;     // rows per CTA
+constexpr int T4_BN = 32;        // columns per tile
+constexpr int T4_N = 16;         // padded right-hand sides
+#ifndef T4_QUNROLL
+#define T4_QUNROLL 1
+#endif
+constexpr int T4_QU = T4_QUNROLL;   // unroll factor of the 4-column groups inside a tile
+
+// shared-memory map (bytes from a 1024-aligned base)
+constexpr uint32_t T4_SC = 0;                  // S^T operand: buffer b at b*32768: hi [128 rows][128 B], lo 16384 B later
+constexpr uint32_t T4_BCH = 65536;             // V of the row block as B operand [16][128 rows] hi: 4 k-blocks x 2048 B
+constexpr uint32_t T4_BCL = 73728;             //                                               lo
+constexpr uint32_t T4_Z = 81920;               // z tiles: 2 stages x 32 x CP floats (<= 4096 B each)
+constexpr uint32_t T4_V = 90112;               // V tiles: 2 stages x 32 x 16 floats (2048 B each)
+constexpr uint32_t T4_BAR = 94208;             // mbarriers
+constexpr uint32_t T4_SMEM_BYTES = T4_BAR + 256 + 1024;
+
+// barrier indices
+constexpr int B_ZFULL = 0;     // [2]  producer -> arithmetic warps (count 1 + tx bytes)
+constexpr int B_ZEMPTY = 2;    // [2]  arithmetic warps -> producer (count 8)
+constexpr int B_SFULL = 4;     // [8 warps][2 buffers]  arithmetic warp w -> issuer (count 1)
+constexpr int B_TDONE = 20;    // [2]  both issuers' tcgen05.commit (count 2): S buffer reusable, D2 readable
+constexpr int B_EREAD = 22;    // [2]  both issuers have read D2 of that buffer (count 2): accumulators reusable
+
+constexpr uint32_t LAYOUT_SW128 = 2, LAYOUT_SW128_BASE32B = 1;
+__device__ __forceinline__ uint64_t smem_desc4(uint32_t saddr, uint32_t lbo_bytes, uint32_t sbo_bytes, uint32_t layout) {
+    return (uint64_t)((saddr >> 4) & 0x3FFF) | ((uint64_t)((lbo_bytes >> 4) & 0x3FFF) << 16) |
+           ((uint64_t)((sbo_bytes >> 4) & 0x3FFF) << 32) | (1ull << 46) | ((uint64_t)layout << 61);
+}
+__host__ __device__ constexpr uint32_t idesc4_tf32(int M, int N, int a_mn_major, int b_mn_major) {
+    return (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)a_mn_major << 15) | ((uint32_t)b_mn_major << 16) |
+           ((uint32_t)(N >> 3) << 17) | ((uint32_t)(M >> 4) << 24);
+}
+__device__ __forceinline__ void umma4(uint32_t d_tmem, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t accumulate) {
+    asm volatile(
+        "{\n\t"
+        ".reg .pred p;\n\t"
+        "setp.ne.b32 p, %4, 0;\n\t"
+        "tcgen05.mma.cta_group::1.kind::tf32 [%0], %1, %2, %3, p;\n\t"
+        "}\n" ::"r"(d_tmem), "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate)
+        : "memory");
+}
+__device__ __forceinline__ void umma4_commit(uint64_t* bar) {
+    asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive4(uint64_t* bar) {
+    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
+// helper warps poll with a back-off so that their spinning does not take issue slots from the arithmetic warps
+__device__ __forceinline__ void mbar_wait_sleep4(uint64_t* bar, uint32_t parity) {
+    uint32_t done = 0;
+    while (true) {
+        asm volatile(
+            "{\n\t.reg .pred p;\n\t"
+            "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+            "selp.u32 %0, 1, 0, p;\n\t}\n"
+            : "=r"(done)
+            : "r"(smem_u32(bar)), "r"(parity)
+            : "memory");
+        if (done) break;
+        __nanosleep(128);
+    }
+}
+__device__ __forceinline__ void tc4_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void tc4_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void fence4_async_smem() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
+__device__ __forceinline__ void tmem4_ld16(uint32_t taddr, float* v) {
+    uint32_t r[16];
+    asm volatile(
+        "tcgen05.ld.sync.aligned.32x32b.x16.b32 {%0,%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15}, [%16];"
+        : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]),
+          "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15])
+        : "r"(taddr));
+    asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+#pragma unroll
+    for (int q = 0; q < 16; ++q) v[q] = __uint_as_float(r[q]);
+}
+__device__ __forceinline__ float tf32_hi4(float x) { return __uint_as_float(__float_as_uint(x) & 0xFFFFE000u); }
+__device__ __forceinline__ uint32_t sw128_4(uint32_t row, uint32_t kk) {
+    return row * 128u + ((((kk >> 2) ^ (row & 7u)) << 4) | ((kk & 3u) << 2));
+}
+
+struct Sym4Args {
+    const float* z;        // [n][CP]
+    const float* v;        // [n][16]
+    const float* nlc;      // [CP]
+    double* acc;           // [n][16] FP64 accumulators (zeroed by the launcher)
+    long long n;
+    int nblocks, half, nsplits, rb_begin;
+};
+
+// tile enumeration shared by all roles: offsets k in [k_begin, k_end), four 32-column tiles per 128-column block
+struct TileIter4 {
+    int I, B, k_begin, ntiles;
+    long long n;
+    __device__ __forceinline__ int block_of(int k) const { int Ip = I + k; return Ip >= B ? Ip - B : Ip; }
+    __device__ __forceinline__ bool offset_active(int k) const { return !((B % 2 == 0) && (k == B / 2) && (I >= B / 2)); }
+    __device__ __forceinline__ long long col0(int t) const { return (long long)block_of(k_begin + (t >> 2)) * T4_ROWS + (t & 3) * T4_BN; }
+    __device__ __forceinline__ bool live(int t) const { return offset_active(k_begin + (t >> 2)) && col0(t) < n; }
+    __device__ __forceinline__ bool diag(int t) const { return block_of(k_begin + (t >> 2)) == I; }
+    __device__ __forceinline__ int next_live(int t) const { while (t < ntiles && !live(t)) ++t; return t; }
+};
+
+}  // namespace
+
+template <int CP, int NP2, int TP>
+__global__ void __launch_bounds__(384, 2) mvm_sym_tc4_kernel(const Sym4Args a) {
+    extern __shared__ unsigned char smem_raw[];
+    const uint32_t base = (smem_u32(smem_raw) + 1023u) & ~1023u;
+    unsigned char* sm = smem_raw + (base - smem_u32(smem_raw));
+    uint64_t* bars = reinterpret_cast<uint64_t*>(sm + T4_BAR);
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(sm + T4_BAR + 224);
+
+    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+    TileIter4 it;
+    it.I = a.rb_begin + blockIdx.x;
+    it.B = a.nblocks;
+    it.n = a.n;
+    const int per = (a.half + a.nsplits - 1) / a.nsplits;
+    it.k_begin = blockIdx.y * per;
+    it.ntiles = 4 * (min(a.half, it.k_begin + per) - it.k_begin);
+    if (it.ntiles < 0) it.ntiles = 0;
+
+    if (tid == 0) {
+        mbar_init(&bars[B_ZFULL + 0], 1);
+        mbar_init(&bars[B_ZFULL + 1], 1);
+        mbar_init(&bars[B_ZEMPTY + 0], 8);
+        mbar_init(&bars[B_ZEMPTY + 1], 8);
+#pragma unroll
+        for (int w = 0; w < 16; ++w) mbar_init(&bars[B_SFULL + w], 1);
+        mbar_init(&bars[B_TDONE + 0], 2);
+        mbar_init(&bars[B_TDONE + 1], 2);
+        mbar_init(&bars[B_EREAD + 0], 2);
+        mbar_init(&bars[B_EREAD + 1], 2);
+        mbar_fence_init();
+    }
+    if (warp == 8) {
+        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], 64;" ::"r"(smem_u32(tmem_slot)) : "memory");
+        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+    }
+    tc4_fence_before();
+    __syncthreads();
+    tc4_fence_after();
+    const uint32_t tmem = *tmem_slot;   // D2[issuer h][buffer b] at column 32*b + 16*h
+
+    if (warp < 8) {
+        // =========================================== arithmetic warps ===================================================
+        asm volatile("setmaxnreg.inc.sync.aligned.u32 96;");
+        constexpr int CPH = CP / 2;                    // coordinates handled by one of the two threads of a row
+        constexpr int TPH = TP / 2;                    // right-hand sides handled by one of the two threads of a row
+        static_assert(CPH % 2 == 0 && TPH % 2 == 0, "halves must be packable");
+        const int half = lane >> 4;                    // which half of the projections / right-hand sides
+        const int rloc = warp * 16 + (lane & 15);      // row inside the 128-row block
+        const long long row = (long long)it.I * T4_ROWS + rloc;
+        const bool valid = row < a.n;
+        f32x2 rz[CPH / 2], rc2[CPH / 2];
+#pragma unroll
+        for (int q = 0; q < CPH / 2; ++q) {
+            const float2 p = valid ? __ldg(reinterpret_cast<const float2*>(a.z + row * CP + half * CPH) + q) : make_float2(0.f, 0.f);
+            rz[q] = pack2(p.x, p.y);
+            rc2[q] = pack2(__ldg(a.nlc + half * CPH + 2 * q), __ldg(a.nlc + half * CPH + 2 * q + 1));
+        }
+        {   // B operand of the column side: V rows of this block, [16 rows c][128 k = row-in-block], K-major SW128;
+            // the first thread of a row writes the tf32-hi plane, the second the remainder plane
+            const int kb = rloc >> 5, kk = rloc & 31;
+#pragma unroll
+            for (int c = 0; c < T4_N; ++c) {
+                const float v = valid ? __ldg(a.v + row * T4_N + c) : 0.f;
+                const float h = tf32_hi4(v);
+                const uint32_t off = (uint32_t)kb * 2048u + (uint32_t)(c >> 3) * 1024u + sw128_4((uint32_t)(c & 7), (uint32_t)kk);
+                *reinterpret_cast<float*>(sm + (half ? T4_BCL : T4_BCH) + off) = half ? (v - h) : h;
+            }
+        }
+        f32x2 acc[TPH / 2], comp[TPH / 2];
+#pragma unroll
+        for (int q = 0; q < TPH / 2; ++q) { acc[q] = 0ull; comp[q] = 0ull; }
+
+        int j = 0, jc = 0;
+        for (int t = it.next_live(0); t < it.ntiles; t = it.next_live(t + 1), ++j) {
+            const int s = j & 1;
+            const long long c0 = it.col0(t);
+            const int cols = (int)min((long long)T4_BN, a.n - c0);
+            const bool diag = it.diag(t);
+            const int bc = jc & 1;
+            mbar_wait(&bars[B_ZFULL + s], (uint32_t)((j >> 1) & 1));
+            if (!diag && jc >= 2) mbar_wait(&bars[B_TDONE + bc], (uint32_t)(((jc >> 1) - 1) & 1));   // S buffer bc is free again
+            const float* zt = reinterpret_cast<const float*>(sm + T4_Z) + (size_t)s * T4_BN * CP + half * CPH;
+            const float* vt = reinterpret_cast<const float*>(sm + T4_V) + (size_t)s * T4_BN * T4_N + half * TPH;
+            unsigned char* sc = sm + T4_SC + (uint32_t)bc * 32768u + (half ? 16384u : 0u);   // hi plane / lo plane
+            f32x2 lo[TPH / 2];
+#pragma unroll
+            for (int q = 0; q < TPH / 2; ++q) lo[q] = 0ull;
+            auto tile_body = [&](auto full_tile) {
+                constexpr bool FULL = decltype(full_tile)::value;
+#pragma unroll 1
+                for (int q = 0; q < T4_BN / 4; ++q) {
+                    float sv[4];
+#pragma unroll
+                    for (int e = 0; e < 4; ++e) {
+                        const int c = 4 * q + e;
+                        const float* zc = zt + c * CP;
+                        f32x2 s0 = 0ull, s1 = 0ull;
+#pragma unroll
+                        for (int p = 0; p < CPH / 2; ++p) {     // this thread's half of the projections
+                            const f32x2 zj = *reinterpret_cast<const f32x2*>(zc + 2 * p);
+                            const f32x2 d = sub2(rz[p], zj);
+                            const f32x2 u = fma2(d, d, rc2[p]);
+                            f32x2 ex;
+                            if (p >= CPH / 2 - NP2) {
+                                ex = exp2_neg_poly2(u);
+                            } else {
+                                float ul, uh;
+                                unpack2(u, ul, uh);
+                                ex = pack2(ex2_ftz(-ul), ex2_ftz(-uh));
+                            }
+                            if (p == 0) s0 = ex; else if (p == 1) s1 = ex; else if (p & 1) s1 = add2(s1, ex); else s0 = add2(s0, ex);
+                        }
+                        float plo, phi;
+                        if constexpr (CPH / 2 >= 2) unpack2(add2(s0, s1), plo, phi); else unpack2(s0, plo, phi);
+                        const float part = plo + phi;
+                        const float val = part + __shfl_xor_sync(0xffffffffu, part, 16);   // the other half of the projections
+                        sv[e] = (FULL || c < cols) ? val : 0.f;      // columns behind a partial tile hold stale bytes
+                        const f32x2 ss = pack2(sv[e], sv[e]);
+#pragma unroll
+                        for (int k = 0; k < TPH / 2; ++k)            // row side, this thread's half of the right-hand sides
+                            lo[k] = fma2(ss, *reinterpret_cast<const f32x2*>(vt + c * T4_N + 2 * k), lo[k]);
+                    }
+                    if (!diag) {   // column side operand, SWIZZLE_128B_BASE32B: first thread of the row stores hi, second stores lo
+                        float4 w;
+                        if (half) {
+                            w.x = sv[0] - tf32_hi4(sv[0]); w.y = sv[1] - tf32_hi4(sv[1]); w.z = sv[2] - tf32_hi4(sv[2]); w.w = sv[3] - tf32_hi4(sv[3]);
+                        } else {
+                            w.x = tf32_hi4(sv[0]); w.y = tf32_hi4(sv[1]); w.z = tf32_hi4(sv[2]); w.w = tf32_hi4(sv[3]);
+                        }
+                        const uint32_t off = (uint32_t)rloc * 128u + (((((uint32_t)q >> 1) ^ ((uint32_t)rloc & 3u)) << 5) | (((uint32_t)q & 1u) << 4));
+                        *reinterpret_cast<float4*>(sc + off) = w;
+                    }
+                }
+            };
+            if (cols == T4_BN) tile_body(std::true_type{}); else tile_body(std::false_type{});
+#pragma unroll
+            for (int q = 0; q < TPH / 2; ++q) {   // Kahan-compensated fold of the tile sum
+                const f32x2 y = sub2(lo[q], comp[q]);
+                const f32x2 tsum = add2(acc[q], y);
+                comp[q] = sub2(sub2(tsum, acc[q]), y);
+                acc[q] = tsum;
+            }
+            if (!diag) {
+                fence4_async_smem();
+                __syncwarp();
+                if (lane == 0) mbar_arrive4(&bars[B_SFULL + warp * 2 + bc]);
+                ++jc;
+            } else {
+                __syncwarp();
+            }
+            if (lane == 0) mbar_arrive4(&bars[B_ZEMPTY + s]);
+        }
+        if (valid && j > 0) {
+            double* dst = a.acc + row * T4_N + half * TPH;
+#pragma unroll
+            for (int q = 0; q < TPH / 2; ++q) {
+                float x, y;
+                unpack2(acc[q], x, y);
+                atomicAdd(dst + 2 * q, (double)x);
+                atomicAdd(dst + 2 * q + 1, (double)y);
+            }
+        }
+    } else {
+        asm volatile("setmaxnreg.dec.sync.aligned.u32 48;");
+        if (warp == 10) {
+            // =========================================== TMA producer ====================================================
+            if (lane == 0) {
+                int j = 0;
+                for (int t = it.next_live(0); t < it.ntiles; t = it.next_live(t + 1), ++j) {
+                    const int s = j & 1;
+                    if (j >= 2) mbar_wait_sleep4(&bars[B_ZEMPTY + s], (uint32_t)(((j >> 1) - 1) & 1));
+                    const long long c0 = it.col0(t);
+                    const uint32_t cols = (uint32_t)min((long long)T4_BN, a.n - c0);
+                    mbar_expect_tx(&bars[B_ZFULL + s], cols * (CP + T4_N) * (uint32_t)sizeof(float));
+                    bulk_g2s(sm + T4_Z + (uint32_t)s * T4_BN * CP * 4u, a.z + c0 * CP, cols * CP * (uint32_t)sizeof(float), &bars[B_ZFULL + s]);
+                    bulk_g2s(sm + T4_V + (uint32_t)s * T4_BN * T4_N * 4u, a.v + c0 * T4_N, cols * T4_N * (uint32_t)sizeof(float), &bars[B_ZFULL + s]);
+                }
+            }
+        } else if (warp == 8 || warp == 9) {
+            // =========================================== MMA issue + column-side epilogue =================================
+            const int h = warp - 8;                      // arithmetic warps 4h .. 4h+3  ->  k-groups 8h .. 8h+7; TMEM lane quadrant h
+            constexpr uint32_t IDESC_COL = idesc4_tf32(64, T4_N, 1, 0);
+            const uint64_t dB_h = smem_desc4(base + T4_BCH, 16, 1024, LAYOUT_SW128), dB_l = smem_desc4(base + T4_BCL, 16, 1024, LAYOUT_SW128);
+            int jc = 0;
+            long long prev_c0 = -1;
+            auto epilogue = [&](int pjc, long long pc0) {
+                const int pb = pjc & 1;
+                mbar_wait_sleep4(&bars[B_TDONE + pb], (uint32_t)((pjc >> 1) & 1));
+                tc4_fence_after();
+                float d0[16], d1[16];
+                const uint32_t lane_base = (uint32_t)(h * 32) << 16;
+                tmem4_ld16(tmem + 32u * pb + lane_base, d0);
+                tmem4_ld16(tmem + 32u * pb + 16u + lane_base, d1);
+                tc4_fence_before();
+                if (lane == 0) mbar_arrive4(&bars[B_EREAD + pb]);
+                const long long crow = pc0 + 16 * h + lane;   // M = 64 layout: rows 16h .. 16h+15 in lanes 0..15 of quadrant h
+                if (lane < 16 && crow < a.n) {
+                    double* dst = a.acc + crow * T4_N;
+#pragma unroll
+                    for (int c = 0; c < T4_N; ++c) atomicAdd(dst + c, (double)d0[c] + (double)d1[c]);
+                }
+            };
+            for (int t = it.next_live(0); t < it.ntiles; t = it.next_live(t + 1)) {
+                if (it.diag(t)) continue;
+                const int bc = jc & 1;
+                if (jc >= 2) mbar_wait_sleep4(&bars[B_EREAD + bc], (uint32_t)(((jc >> 1) - 1) & 1));   // both issuers have read D2 of tile jc-2
+                const uint32_t d2 = tmem + 32u * bc + 16u * h;
+                const uint64_t dA_h = smem_desc4(base + T4_SC + (uint32_t)bc * 32768u, 16384, 512, LAYOUT_SW128_BASE32B);
+                const uint64_t dA_l = smem_desc4(base + T4_SC + (uint32_t)bc * 32768u + 16384u, 16384, 512, LAYOUT_SW128_BASE32B);
+#pragma unroll 1
+                for (int sw = 4 * h; sw < 4 * h + 4; ++sw) {
+                    mbar_wait_sleep4(&bars[B_SFULL + sw * 2 + bc], (uint32_t)((jc >> 1) & 1));
+                    tc4_fence_after();
+                    if (lane == 0) {
+#pragma unroll
+                        for (int gl = 0; gl < 2; ++gl) {
+                            const int g = 2 * sw + gl;
+                            const uint64_t aoff = (uint64_t)((g * 1024) >> 4);
+                            const uint64_t boff = (uint64_t)(((g >> 2) * 2048 + (g & 3) * 32) >> 4);
+                            umma4(d2, dA_h + aoff, dB_h + boff, IDESC_COL, (sw > 4 * h || gl > 0) ? 1u : 0u);
+                            umma4(d2, dA_l + aoff, dB_h + boff, IDESC_COL, 1);
+                            umma4(d2, dA_h + aoff, dB_l + boff, IDESC_COL, 1);
+                        }
+                    }
+                    __syncwarp();
+                }
+                if (lane == 0) umma4_commit(&bars[B_TDONE + bc]);
+                __syncwarp();
+                if (prev_c0 >= 0) epilogue(jc - 1, prev_c0);
+                prev_c0 = it.col0(t);
+                ++jc;
+            }
+            if (prev_c0 >= 0) epilogue(jc - 1, prev_c0);
+        }
+    }
+    tc4_fence_before();
+    __syncthreads();
+    if (warp == 8) {
+        asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, 64;" ::"r"(tmem) : "memory");
+    }
+}
+
+template <int CP, int NP2, int TP>
+static int run_sym4(const Sym4Args& a, dim3 grid, cudaStream_t st) {
+    auto kernel = mvm_sym_tc4_kernel<CP, NP2, TP>;
+    cudaError_t e = cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)T4_SMEM_BYTES);
+    if (e != cudaSuccess) return cuda_fail(e, "cudaFuncSetAttribute(mvm_sym_tc4_kernel)");
+    kernel<<<grid, 384, T4_SMEM_BYTES, st>>>(a);
+    note_launch();
+    return cuda_fail(cudaGetLastError(), "mvm_sym_tc4_kernel launch");
+}
+
+__global__ void sym4_finalize_kernel(const double* __restrict__ acc, long long n, int t, float* __restrict__ out, int ldo) {
+    const long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (idx >= n * t) return;
+    const long long row = idx / t;
+    const int c = (int)(idx - row * t);
+    out[row * ldo + c] = (float)acc[row * T4_N + c];
+}
+
+int launch_sym_tc4(const float* zp, long long n, int CP, const float* nlc, const float* V16, int t, float* out, int ldo,
+                   int rb_begin, int rb_end, void* workspace, size_t workspace_bytes, cudaStream_t st) {
+    const size_t need = (size_t)n * T4_N * sizeof(double);
+    if (workspace == nullptr || workspace_bytes < need) {
+        set_error("mvm_sym: workspace %zu bytes < required %zu", workspace_bytes, need);
+        return ERR_WORKSPACE;
+    }
+    double* acc = (double*)workspace;
+    RPGP_CUDA_OK(cudaMemsetAsync(acc, 0, need, st));
+    Sym4Args a;
+    a.z = zp; a.v = V16; a.nlc = nlc; a.acc = acc; a.n = n;
+    a.nblocks = (int)((n + T4_ROWS - 1) / T4_ROWS);
+    a.half = a.nblocks / 2 + 1;
+    a.rb_begin = rb_begin;
+    const int nrb = rb_end - rb_begin;
+    if (nrb > 0) {
+        static const int splits_env = [] { const char* e = getenv("RPGP_SYM_SPLITS"); return e ? atoi(e) : 0; }();
+        long long want = (148LL * 2 * 16 + nrb - 1) / nrb;
+        if (splits_env > 0) want = splits_env;
+        want = std::max<long long>(1, std::min<long long>(want, a.half));
+        a.nsplits = (int)want;
+        dim3 grid((unsigned)nrb, (unsigned)a.nsplits, 1);
+        // polynomial-exp2 pairs: this kernel is bound by instruction issue (an FFMA2 takes two issue cycles), so fewer pairs
+        // go to the FMA pipe than in the forward kernel; RPGP_SYM_POLY_PAIRS overrides (tools sweep)
+        static const int np_env = [] { const char* e = getenv("RPGP_SYM_POLY_PAIRS"); return e ? atoi(e) : -1; }();
+        const int tp = t <= 4 ? 4 : (t <= 8 ? 8 : (t <= 12 ? 12 : 16));
+        int rc = ERR_UNSUPPORTED;
+#define RPGP_SYM4_CASE(CPv, NPv)                                                                              \
+        if (CP == CPv && np == NPv) {                                                                         \
+            rc = tp == 4 ? run_sym4<CPv, NPv, 4>(a, grid, st) : tp == 8 ? run_sym4<CPv, NPv, 8>(a, grid, st)    \
+                 : tp == 12 ? run_sym4<CPv, NPv, 12>(a, grid, st) : run_sym4<CPv, NPv, 16>(a, grid, st);       \
+        }
+        const int np = np_env >= 0 ? np_env : (CP >= 16 ? 1 : 0);   // polynomial pairs PER THREAD (two threads per row)
+        RPGP_SYM4_CASE(4, 0) RPGP_SYM4_CASE(8, 0) RPGP_SYM4_CASE(12, 0) RPGP_SYM4_CASE(16, 0) RPGP_SYM4_CASE(16, 1)
+        RPGP_SYM4_CASE(20, 0) RPGP_SYM4_CASE(20, 1) RPGP_SYM4_CASE(24, 0) RPGP_SYM4_CASE(24, 1)
+        RPGP_SYM4_CASE(28, 0) RPGP_SYM4_CASE(28, 1) RPGP_SYM4_CASE(32, 0) RPGP_SYM4_CASE(32, 1)
+#undef RPGP_SYM4_CASE
+        if (rc == ERR_UNSUPPORTED) set_error("mvm_sym: no kernel for CP=%d poly pairs=%d", CP, np);
+        if (rc) return rc;
+    }
+    const long long total = n * t;
+    sym4_finalize_kernel<<<(unsigned)((total + 255) / 256), 256, 0, st>>>(acc, n, t, out, ldo);
+    note_launch();
+    return cuda_fail(cudaGetLastError(), "sym4_finalize_kernel");
+}
+
+}  // namespace rpgp
