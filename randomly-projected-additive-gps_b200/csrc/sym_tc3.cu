@@ -397,10 +397,10 @@ int launch_sym_tc3(const float* zp, long long n, int CP, const float* nlc, const
         }
         const int np = np_env >= 0 ? np_env : (CP >= 20 ? 2 : (CP >= 16 ? 1 : 0));
         RPGP_SYM3_CASE(4, 0) RPGP_SYM3_CASE(8, 0) RPGP_SYM3_CASE(12, 0) RPGP_SYM3_CASE(16, 0) RPGP_SYM3_CASE(16, 1)
-        RPGP_SYM3_CASE(20, 0) RPGP_SYM3_CASE(20, 1) RPGP_SYM3_CASE(20, 2) RPGP_SYM3_CASE(24, 0) RPGP_SYM3_CASE(24, 1)
-        RPGP_SYM3_CASE(28, 0) RPGP_SYM3_CASE(28, 1) RPGP_SYM3_CASE(32, 0) RPGP_SYM3_CASE(32, 1) RPGP_SYM3_CASE(32, 2)
+        RPGP_SYM3_CASE(20, 0) RPGP_SYM3_CASE(20, 1) RPGP_SYM3_CASE(20, 2) RPGP_SYM3_CASE(24, 0) RPGP_SYM3_CASE(24, 2)
+        RPGP_SYM3_CASE(28, 0) RPGP_SYM3_CASE(28, 2) RPGP_SYM3_CASE(32, 0) RPGP_SYM3_CASE(32, 2)
 #undef RPGP_SYM3_CASE
-        if (rc == ERR_UNSUPPORTED) set_error("mvm_sym: no kernel for CP=%d poly pairs=%d", CP, np);
+        if (rc == ERR_UNSUPPORTED) set_error("mvm_sym: no kernel for CP=%d poly pairs=%d (compiled: 0 for every CP, 1 for CP 16/20, 2 for CP >= 20)", CP, np);
         if (rc) return rc;
     }
     const long long total = n * t;
