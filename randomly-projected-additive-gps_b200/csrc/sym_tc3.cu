@@ -36,8 +36,7 @@ constexpr int T3_QU = T3_QUNROLL;   // unroll factor of the 4-column groups insi
 
 // shared-memory map (bytes from a 1024-aligned base)
 constexpr uint32_t T3_SC = 0;                  // S^T operand: buffer b at b*32768: hi [128 rows][128 B], lo 16384 B later
-constexpr uint32_t T3_BCH = 65536;             // V of the row block as B operand [16][128 rows] hi: 4 k-blocks x 2048 B
-constexpr uint32_t T3_BCL = 73728;             //                                               lo
+constexpr uint32_t T3_BC = 65536;              // V of the row block as B operand [32 = 16 hi rows + 16 lo rows][128 k]: 4 k-blocks x 4096 B
 constexpr uint32_t T3_Z = 81920;               // z tiles: 2 stages x 32 x CP floats (<= 4096 B each)
 constexpr uint32_t T3_V = 90112;               // V tiles: 2 stages x 32 x 16 floats (2048 B each)
 constexpr uint32_t T3_BAR = 94208;             // mbarriers
@@ -164,13 +163,13 @@ __global__ void __launch_bounds__(256, 2) mvm_sym_tc3_kernel(const Sym3Args a) {
         mbar_fence_init();
     }
     if (warp == 4) {
-        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], 64;" ::"r"(smem_u32(tmem_slot)) : "memory");
+        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], 128;" ::"r"(smem_u32(tmem_slot)) : "memory");
         asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
     }
     tc3_fence_before();
     __syncthreads();
     tc3_fence_after();
-    const uint32_t tmem = *tmem_slot;   // D2[issuer h][buffer b] at column 32*b + 16*h
+    const uint32_t tmem = *tmem_slot;   // D2[issuer h][buffer b]: 32 columns (Sh.Vh + Sl.Vh | Sh.Vl) at column 64*b + 32*h
 
     if (warp < 4) {
         // =========================================== arithmetic warps ===================================================
@@ -185,9 +184,9 @@ __global__ void __launch_bounds__(256, 2) mvm_sym_tc3_kernel(const Sym3Args a) {
             for (int c = 0; c < T3_N; ++c) {
                 const float v = valid ? __ldg(a.v + row * T3_N + c) : 0.f;
                 const float h = tf32_hi3(v);
-                const uint32_t off = (uint32_t)kb * 2048u + (uint32_t)(c >> 3) * 1024u + sw128_3((uint32_t)(c & 7), (uint32_t)kk);
-                *reinterpret_cast<float*>(sm + T3_BCH + off) = h;
-                *reinterpret_cast<float*>(sm + T3_BCL + off) = v - h;
+                const uint32_t off = (uint32_t)kb * 4096u + (uint32_t)(c >> 3) * 1024u + sw128_3((uint32_t)(c & 7), (uint32_t)kk);
+                *reinterpret_cast<float*>(sm + T3_BC + off) = h;                 // rows 0..15: tf32-hi part
+                *reinterpret_cast<float*>(sm + T3_BC + 2048u + off) = v - h;     // rows 16..31: remainder
             }
         }
         f32x2 acc[TP / 2], comp[TP / 2];   // TP = right-hand sides rounded up to 4 (row side only; the MMA N stays 16)
@@ -284,8 +283,9 @@ __global__ void __launch_bounds__(256, 2) mvm_sym_tc3_kernel(const Sym3Args a) {
         } else if (warp == 4 || warp == 5) {
             // =========================================== MMA issue + column-side epilogue =================================
             const int h = warp - 4;                      // arithmetic warps 2h, 2h+1  ->  k-groups 8h .. 8h+7; TMEM lane quadrant h
-            constexpr uint32_t IDESC_COL = idesc3_tf32(64, T3_N, 1, 0);
-            const uint64_t dB_h = smem_desc3(base + T3_BCH, 16, 1024, LAYOUT_SW128), dB_l = smem_desc3(base + T3_BCL, 16, 1024, LAYOUT_SW128);
+            // two MMAs per k-step instead of three: Sh.[Vh | Vl] (N = 32) and Sl.Vh (N = 16, into the first 16 columns)
+            constexpr uint32_t IDESC_N32 = idesc3_tf32(64, 2 * T3_N, 1, 0), IDESC_N16 = idesc3_tf32(64, T3_N, 1, 0);
+            const uint64_t dB = smem_desc3(base + T3_BC, 16, 1024, LAYOUT_SW128);
             int jc = 0;
             long long prev_c0 = -1;
             auto epilogue = [&](int pjc, long long pc0) {
@@ -294,8 +294,15 @@ __global__ void __launch_bounds__(256, 2) mvm_sym_tc3_kernel(const Sym3Args a) {
                 tc3_fence_after();
                 float d0[16], d1[16];
                 const uint32_t lane_base = (uint32_t)(h * 32) << 16;
-                tmem3_ld16(tmem + 32u * pb + lane_base, d0);
-                tmem3_ld16(tmem + 32u * pb + 16u + lane_base, d1);
+                {   // sum of the four 16-column pieces: two issuers x (Sh.Vh + Sl.Vh | Sh.Vl)
+                    float e0[16], e1[16];
+                    tmem3_ld16(tmem + 64u * pb + lane_base, d0);
+                    tmem3_ld16(tmem + 64u * pb + 16u + lane_base, e0);
+                    tmem3_ld16(tmem + 64u * pb + 32u + lane_base, d1);
+                    tmem3_ld16(tmem + 64u * pb + 48u + lane_base, e1);
+#pragma unroll
+                    for (int c = 0; c < 16; ++c) { d0[c] += e0[c]; d1[c] += e1[c]; }
+                }
                 tc3_fence_before();
                 if (lane == 0) mbar_arrive(&bars[B_EREAD + pb]);
                 const long long crow = pc0 + 16 * h + lane;   // M = 64 layout: rows 16h .. 16h+15 in lanes 0..15 of quadrant h
@@ -309,7 +316,7 @@ __global__ void __launch_bounds__(256, 2) mvm_sym_tc3_kernel(const Sym3Args a) {
                 if (it.diag(t)) continue;
                 const int bc = jc & 1;
                 if (jc >= 2) mbar_wait_sleep(&bars[B_EREAD + bc], (uint32_t)(((jc >> 1) - 1) & 1));   // both issuers have read D2 of tile jc-2
-                const uint32_t d2 = tmem + 32u * bc + 16u * h;
+                const uint32_t d2 = tmem + 64u * bc + 32u * h;
                 const uint64_t dA_h = smem_desc3(base + T3_SC + (uint32_t)bc * 32768u, 16384, 512, LAYOUT_SW128_BASE32B);
                 const uint64_t dA_l = smem_desc3(base + T3_SC + (uint32_t)bc * 32768u + 16384u, 16384, 512, LAYOUT_SW128_BASE32B);
 #pragma unroll 1
@@ -321,10 +328,9 @@ __global__ void __launch_bounds__(256, 2) mvm_sym_tc3_kernel(const Sym3Args a) {
                         for (int gl = 0; gl < 4; ++gl) {
                             const int g = 4 * sw + gl;
                             const uint64_t aoff = (uint64_t)((g * 1024) >> 4);
-                            const uint64_t boff = (uint64_t)(((g >> 2) * 2048 + (g & 3) * 32) >> 4);
-                            umma3(d2, dA_h + aoff, dB_h + boff, IDESC_COL, (sw > 2 * h || gl > 0) ? 1u : 0u);
-                            umma3(d2, dA_l + aoff, dB_h + boff, IDESC_COL, 1);
-                            umma3(d2, dA_h + aoff, dB_l + boff, IDESC_COL, 1);
+                            const uint64_t boff = (uint64_t)(((g >> 2) * 4096 + (g & 3) * 32) >> 4);
+                            umma3(d2, dA_h + aoff, dB + boff, IDESC_N32, (sw > 2 * h || gl > 0) ? 1u : 0u);
+                            umma3(d2, dA_l + aoff, dB + boff, IDESC_N16, 1);
                         }
                     }
                     __syncwarp();
@@ -341,7 +347,7 @@ __global__ void __launch_bounds__(256, 2) mvm_sym_tc3_kernel(const Sym3Args a) {
     tc3_fence_before();
     __syncthreads();
     if (warp == 4) {
-        asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, 64;" ::"r"(tmem) : "memory");
+        asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, 128;" ::"r"(tmem) : "memory");
     }
 }
 
