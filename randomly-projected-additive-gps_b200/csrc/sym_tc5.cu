@@ -1,0 +1,461 @@
+// sym_tc5.cu -- symmetric K(Z,Z).V with BOTH uses of every kernel value on the tensor cores.
+//
+// Every kernel value k(i,i') of a 128-row x 32-column tile is computed ONCE by the arithmetic warps (thread = row), split into
+// its tf32 part and the remainder (3xTF32) and written to shared memory in ONE layout (SWIZZLE_128B_BASE32B, row-local stores).
+// tcgen05.mma kind::tf32 then reads that single copy twice (profiles/umma_microbench_r01.txt, umma_probe3):
+//     row side     out[i ,:] += sum_i' k(i,i') V[i',:]     A = S    K-major  (M = 128 rows,  K = 8 tile columns per MMA)
+//     column side  out[i',:] += sum_i  k(i,i') V[i ,:]     A = S^T  MN-major (M = 64 = 32 columns of the tf32 part stacked on the
+//                                                                             32 columns of the remainder, K = 8 tile rows per MMA)
+// so the arithmetic warps no longer read V or spend FFMA2 issue slots on it (the kernel is issue-bound, ncu_r01_sym_cfg2_summary.md).
+// The right-hand sides arrive pre-split and pre-swizzled as B operands ([16 tf32 parts | 16 remainders] x 32 rows per 4 KB block,
+// written once per launch by sym5_split_rhs_kernel) and are moved by the TMA engine like the coordinate tiles.
+//
+// Accumulation: the row side accumulates T5_F tiles in TMEM (double-buffered by epoch), the owning arithmetic warp folds each epoch
+// into Kahan-compensated FP32 registers; the column side is read back per tile by four epilogue warps (TMEM lane quadrants 0..3),
+// combined through shared memory and added to FP64 accumulators with coalesced atomics.
+//
+// CTA = 256 threads: warps 0-3 arithmetic (setmaxnreg.inc), warps 4-7 epilogue (setmaxnreg.dec); lane 0 of warp 4 also issues the
+// MMAs of a tile, lane 0 of warp 5 also issues the bulk copies (all buffers are released by the tile's tcgen05.commit).
+#include <algorithm>
+#include <cstdlib>
+
+#include "aux_kernels.cuh"
+#include "kv_kernels.cuh"
+#include "sym_tc.cuh"
+
+namespace rpgp {
+
+namespace {
+
+constexpr int T5_ROWS = 128;     // rows per CTA
+constexpr int T5_BN = 32;        // columns per tile
+constexpr int T5_N = 16;         // padded right-hand sides
+constexpr int T5_F = 4;          // tiles accumulated in TMEM per row-side epoch (K = 128 per flush, like the column side)
+constexpr int T5_ZST = 3;        // coordinate-tile stages
+#ifndef T5_REGS_ARITH
+#define T5_REGS_ARITH 184
+#endif
+#ifndef T5_REGS_HELP
+#define T5_REGS_HELP 72
+#endif
+
+// shared-memory map (bytes from a 1024-aligned base)
+constexpr uint32_t T5_S = 0;                    // S operand: buffer b at b*32768: tf32 part [128 rows][128 B], remainder 16384 B later
+constexpr uint32_t T5_BC = 65536;               // B operand of the column side: V of this row block, 4 blocks x 4096 B
+constexpr uint32_t T5_BT = 81920;               // B operand of the row side: V of the tile's columns, 2 stages x 4096 B
+constexpr uint32_t T5_Z = 90112;                // coordinate tiles: 3 stages x 32 x CP floats (<= 4096 B each)
+constexpr uint32_t T5_EPI = 102400;             // column-side epilogue exchange: 2 x [4 quadrants][16 rows][16] floats
+constexpr uint32_t T5_BAR = 110592;             // mbarriers
+constexpr uint32_t T5_SMEM_BYTES = T5_BAR + 256 + 1024;
+
+// barrier indices
+constexpr int B5_ZFULL = 0;      // [3]  bulk copy -> arithmetic warps
+constexpr int B5_BFULL = 3;      // [2]  bulk copy -> MMA issuer (row-side B tile)
+constexpr int B5_SFULL = 5;      // [2]  arithmetic warps -> MMA issuer (count 4)
+constexpr int B5_TDONE = 7;      // [2]  tcgen05.commit of a tile: S / B / z stages reusable, D2 readable, D1 of a closed epoch readable
+constexpr int B5_EREAD = 9;      // [2]  epilogue warps have read D2 (count 4)
+constexpr int B5_D1EMPTY = 11;   // [2]  arithmetic warps have folded an epoch of D1 (count 4)
+constexpr int B5_BCFULL = 13;    // [1]  bulk copy of the column-side B operand
+
+constexpr uint32_t LAYOUT5_SW128 = 2, LAYOUT5_SW128_BASE32B = 1;
+__device__ __forceinline__ uint64_t smem_desc5(uint32_t saddr, uint32_t lbo_bytes, uint32_t sbo_bytes, uint32_t layout) {
+    return (uint64_t)((saddr >> 4) & 0x3FFF) | ((uint64_t)((lbo_bytes >> 4) & 0x3FFF) << 16) |
+           ((uint64_t)((sbo_bytes >> 4) & 0x3FFF) << 32) | (1ull << 46) | ((uint64_t)layout << 61);
+}
+__host__ __device__ constexpr uint32_t idesc5_tf32(int M, int N, int a_mn_major, int b_mn_major) {
+    return (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)a_mn_major << 15) | ((uint32_t)b_mn_major << 16) |
+           ((uint32_t)(N >> 3) << 17) | ((uint32_t)(M >> 4) << 24);
+}
+__device__ __forceinline__ void umma5(uint32_t d_tmem, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t accumulate) {
+    asm volatile(
+        "{\n\t"
+        ".reg .pred p;\n\t"
+        "setp.ne.b32 p, %4, 0;\n\t"
+        "tcgen05.mma.cta_group::1.kind::tf32 [%0], %1, %2, %3, p;\n\t"
+        "}\n" ::"r"(d_tmem), "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate)
+        : "memory");
+}
+__device__ __forceinline__ void umma5_commit(uint64_t* bar) {
+    asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
+__device__ __forceinline__ void mbar5_arrive(uint64_t* bar) {
+    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
+// helper warps poll with a back-off so that their spinning does not take issue slots from the arithmetic warps
+__device__ __forceinline__ void mbar5_wait_sleep(uint64_t* bar, uint32_t parity) {
+    uint32_t done = 0;
+    while (true) {
+        asm volatile(
+            "{\n\t.reg .pred p;\n\t"
+            "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+            "selp.u32 %0, 1, 0, p;\n\t}\n"
+            : "=r"(done)
+            : "r"(smem_u32(bar)), "r"(parity)
+            : "memory");
+        if (done) break;
+        __nanosleep(64);
+    }
+}
+__device__ __forceinline__ void tc5_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void tc5_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void fence5_async_smem() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
+__device__ __forceinline__ void tmem5_ld16(uint32_t taddr, float* v) {
+    uint32_t r[16];
+    asm volatile(
+        "tcgen05.ld.sync.aligned.32x32b.x16.b32 {%0,%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15}, [%16];"
+        : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]),
+          "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15])
+        : "r"(taddr));
+    asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+#pragma unroll
+    for (int q = 0; q < 16; ++q) v[q] = __uint_as_float(r[q]);
+}
+__device__ __forceinline__ float tf32_hi5(float x) { return __uint_as_float(__float_as_uint(x) & 0xFFFFE000u); }
+__host__ __device__ __forceinline__ uint32_t sw128_5(uint32_t row, uint32_t kk) {
+    return row * 128u + ((((kk >> 2) ^ (row & 7u)) << 4) | ((kk & 3u) << 2));
+}
+
+struct Sym5Args {
+    const float* z;        // [n][CP]
+    const float* bsplit;   // [nblocks*4][4096 B] pre-split right-hand sides (B operands)
+    const float* nlc;      // [CP]
+    double* acc;           // [n][16] FP64 accumulators (zeroed by the launcher)
+    long long n;
+    int nblocks, half, nsplits, rb_begin;
+};
+
+// tile enumeration shared by all roles: offsets k in [k_begin, k_end), four 32-column tiles per 128-column block
+struct Tile5Iter {
+    int I, B, k_begin, ntiles;
+    long long n;
+    __device__ __forceinline__ int block_of(int k) const { int Ip = I + k; return Ip >= B ? Ip - B : Ip; }
+    __device__ __forceinline__ bool offset_active(int k) const { return !((B % 2 == 0) && (k == B / 2) && (I >= B / 2)); }
+    __device__ __forceinline__ long long col0(int t) const { return (long long)block_of(k_begin + (t >> 2)) * T5_ROWS + (t & 3) * T5_BN; }
+    __device__ __forceinline__ bool live(int t) const { return offset_active(k_begin + (t >> 2)) && col0(t) < n; }
+    __device__ __forceinline__ bool diag(int t) const { return block_of(k_begin + (t >> 2)) == I; }
+    __device__ __forceinline__ int next_live(int t) const { while (t < ntiles && !live(t)) ++t; return t; }
+};
+
+}  // namespace
+
+template <int CP, int NP2>
+__global__ void __launch_bounds__(256, 2) mvm_sym_tc5_kernel(const Sym5Args a) {
+    extern __shared__ unsigned char smem_raw[];
+    const uint32_t base = (smem_u32(smem_raw) + 1023u) & ~1023u;
+    unsigned char* sm = smem_raw + (base - smem_u32(smem_raw));
+    uint64_t* bars = reinterpret_cast<uint64_t*>(sm + T5_BAR);
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(sm + T5_BAR + 192);
+
+    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+    Tile5Iter it;
+    it.I = a.rb_begin + blockIdx.x;
+    it.B = a.nblocks;
+    it.n = a.n;
+    const int per = (a.half + a.nsplits - 1) / a.nsplits;
+    it.k_begin = blockIdx.y * per;
+    it.ntiles = 4 * (min(a.half, it.k_begin + per) - it.k_begin);
+    if (it.ntiles < 0) it.ntiles = 0;
+
+    if (tid == 0) {
+#pragma unroll
+        for (int s = 0; s < T5_ZST; ++s) mbar_init(&bars[B5_ZFULL + s], 1);
+#pragma unroll
+        for (int b = 0; b < 2; ++b) {
+            mbar_init(&bars[B5_BFULL + b], 1);
+            mbar_init(&bars[B5_SFULL + b], 4);
+            mbar_init(&bars[B5_TDONE + b], 1);
+            mbar_init(&bars[B5_EREAD + b], 4);
+            mbar_init(&bars[B5_D1EMPTY + b], 4);
+        }
+        mbar_init(&bars[B5_BCFULL], 1);
+        mbar_fence_init();
+    }
+    if (warp == 4) {
+        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], 128;" ::"r"(smem_u32(tmem_slot)) : "memory");
+        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+    }
+    tc5_fence_before();
+    __syncthreads();
+    tc5_fence_after();
+    const uint32_t tmem = *tmem_slot;   // D1[epoch & 1] (row side, 128 lanes x 32 columns) at column 32*(epoch&1); D2[b] at 64 + 32*b
+
+    if (warp < 4) {
+        // =========================================== arithmetic warps ===================================================
+        asm volatile("setmaxnreg.inc.sync.aligned.u32 %0;" ::"n"(T5_REGS_ARITH));
+        const long long row = (long long)it.I * T5_ROWS + tid;
+        const bool valid = row < a.n;
+        RowCoords<CP, 1, CP> r;
+        load_row_coords<CP, 1, CP>(r, a.z + row * CP, valid, a.nlc);
+        f32x2 acc[T5_N / 2], comp[T5_N / 2];
+#pragma unroll
+        for (int q = 0; q < T5_N / 2; ++q) { acc[q] = 0ull; comp[q] = 0ull; }
+
+        // fold one closed epoch of the row-side accumulator (this warp's 32 TMEM lanes = its own rows) into the running total
+        auto fold_epoch = [&](int e) {
+            float d[16], x[16];
+            const uint32_t ta = tmem + 32u * (uint32_t)(e & 1) + ((uint32_t)(warp * 32) << 16);
+            tmem5_ld16(ta, d);          // Sh.Vh + Sl.Vh
+            tmem5_ld16(ta + 16u, x);    // Sh.Vl
+            tc5_fence_before();
+            __syncwarp();
+            if (lane == 0) mbar5_arrive(&bars[B5_D1EMPTY + (e & 1)]);
+#pragma unroll
+            for (int q = 0; q < T5_N / 2; ++q) {
+                const f32x2 y = sub2(pack2(d[2 * q] + x[2 * q], d[2 * q + 1] + x[2 * q + 1]), comp[q]);
+                const f32x2 tsum = add2(acc[q], y);
+                comp[q] = sub2(sub2(tsum, acc[q]), y);
+                acc[q] = tsum;
+            }
+        };
+
+        int j = 0, folded = 0;
+        for (int t = it.next_live(0); t < it.ntiles; t = it.next_live(t + 1), ++j) {
+            const int zs = j % T5_ZST, b = j & 1;
+            const long long c0 = it.col0(t);
+            const int cols = (int)min((long long)T5_BN, a.n - c0);
+            mbar_wait(&bars[B5_ZFULL + zs], (uint32_t)((j / T5_ZST) & 1));
+            if (j >= 2) {   // tile j-2 has left the tensor core: S buffer b is free, and every epoch that ended at or before j-2 is closed
+                mbar_wait(&bars[B5_TDONE + b], (uint32_t)(((j >> 1) - 1) & 1));
+                tc5_fence_after();
+                if (j >= T5_F + 1 && (j - 1) % T5_F == 0) fold_epoch(folded++);
+            }
+            const float* zt = reinterpret_cast<const float*>(sm + T5_Z) + (size_t)zs * T5_BN * CP;
+            unsigned char* sc = sm + T5_S + (uint32_t)b * 32768u;
+            auto tile_body = [&](auto full_tile) {
+                constexpr bool FULL = decltype(full_tile)::value;
+#pragma unroll 1
+                for (int q = 0; q < T5_BN / 4; ++q) {
+                    float sv[4];
+#pragma unroll
+                    for (int e = 0; e < 4; ++e) {
+                        const int c = 4 * q + e;
+                        const float val = pair_kernel_value<CP, 1, CP, NP2>(r, zt + c * CP);
+                        sv[e] = (FULL || c < cols) ? val : 0.f;      // columns behind a partial tile hold stale bytes
+                    }
+                    // split, SWIZZLE_128B_BASE32B (32-byte chunks ^ row % 4), row-local stores
+                    float4 h, l;
+                    h.x = tf32_hi5(sv[0]); h.y = tf32_hi5(sv[1]); h.z = tf32_hi5(sv[2]); h.w = tf32_hi5(sv[3]);
+                    l.x = sv[0] - h.x; l.y = sv[1] - h.y; l.z = sv[2] - h.z; l.w = sv[3] - h.w;
+                    const uint32_t off = (uint32_t)tid * 128u + (((((uint32_t)q >> 1) ^ ((uint32_t)tid & 3u)) << 5) | (((uint32_t)q & 1u) << 4));
+                    *reinterpret_cast<float4*>(sc + off) = h;
+                    *reinterpret_cast<float4*>(sc + 16384u + off) = l;
+                }
+            };
+            if (cols == T5_BN) tile_body(std::true_type{}); else tile_body(std::false_type{});
+            fence5_async_smem();
+            __syncwarp();
+            if (lane == 0) mbar5_arrive(&bars[B5_SFULL + b]);
+        }
+        if (j > 0) {
+            mbar_wait(&bars[B5_TDONE + ((j - 1) & 1)], (uint32_t)(((j - 1) >> 1) & 1));   // the last commit covers every earlier MMA
+            tc5_fence_after();
+            const int epochs = (j + T5_F - 1) / T5_F;
+            while (folded < epochs) fold_epoch(folded++);
+            if (valid) {
+                double* dst = a.acc + row * T5_N;
+#pragma unroll
+                for (int q = 0; q < T5_N / 2; ++q) {
+                    float x, y;
+                    unpack2(acc[q], x, y);
+                    atomicAdd(dst + 2 * q, (double)x);
+                    atomicAdd(dst + 2 * q + 1, (double)y);
+                }
+            }
+        }
+    } else {
+        // =========================================== epilogue warps (+ MMA issue, + bulk copies) ========================
+        asm volatile("setmaxnreg.dec.sync.aligned.u32 %0;" ::"n"(T5_REGS_HELP));
+        const int qd = warp - 4;                                   // TMEM lane quadrant
+        const bool issuer = (warp == 4 && lane == 0), loader = (warp == 5 && lane == 0);
+        constexpr uint32_t IDESC_ROW_N32 = idesc5_tf32(128, 2 * T5_N, 0, 0), IDESC_ROW_N16 = idesc5_tf32(128, T5_N, 0, 0);
+        constexpr uint32_t IDESC_COL = idesc5_tf32(64, 2 * T5_N, 1, 0);
+        const unsigned char* bsplit = reinterpret_cast<const unsigned char*>(a.bsplit);
+
+        // the loader runs ahead of the consumers: coordinate tiles three deep, B tiles two deep
+        int tz = it.next_live(0), jz = 0, tb = tz, jb = 0;
+        auto load_z = [&]() {
+            const long long c0 = it.col0(tz);
+            const uint32_t cols = (uint32_t)min((long long)T5_BN, a.n - c0);
+            const int zs = jz % T5_ZST;
+            mbar_expect_tx(&bars[B5_ZFULL + zs], cols * CP * (uint32_t)sizeof(float));
+            bulk_g2s(sm + T5_Z + (uint32_t)zs * T5_BN * CP * 4u, a.z + c0 * CP, cols * CP * (uint32_t)sizeof(float), &bars[B5_ZFULL + zs]);
+            tz = it.next_live(tz + 1);
+            ++jz;
+        };
+        auto load_b = [&]() {
+            const long long c0 = it.col0(tb);
+            const int bs = jb & 1;
+            mbar_expect_tx(&bars[B5_BFULL + bs], 4096u);
+            bulk_g2s(sm + T5_BT + (uint32_t)bs * 4096u, bsplit + (c0 / T5_BN) * 4096, 4096u, &bars[B5_BFULL + bs]);
+            tb = it.next_live(tb + 1);
+            ++jb;
+        };
+        if (loader && tz < it.ntiles) {   // (a CTA without tiles must not leave copies in flight)
+            mbar_expect_tx(&bars[B5_BCFULL], 16384u);
+            bulk_g2s(sm + T5_BC, bsplit + (long long)it.I * 16384, 16384u, &bars[B5_BCFULL]);
+            for (int s = 0; s < T5_ZST && tz < it.ntiles; ++s) load_z();
+            for (int s = 0; s < 2 && tb < it.ntiles; ++s) load_b();
+        }
+
+        int j = 0, jc = 0;
+        for (int t = it.next_live(0); t < it.ntiles; t = it.next_live(t + 1), ++j) {
+            const int b = j & 1;
+            const bool diag = it.diag(t);
+            if (issuer) {
+                const int e = j / T5_F;
+                mbar5_wait_sleep(&bars[B5_BFULL + b], (uint32_t)((j >> 1) & 1));
+                if (j == 0) mbar5_wait_sleep(&bars[B5_BCFULL], 0u);
+                if (j >= 2) mbar5_wait_sleep(&bars[B5_EREAD + b], (uint32_t)(((j >> 1) - 1) & 1));        // D2[b] has been read
+                if (j % T5_F == 0 && e >= 2) mbar5_wait_sleep(&bars[B5_D1EMPTY + (e & 1)], (uint32_t)(((e >> 1) - 1) & 1));
+                mbar5_wait_sleep(&bars[B5_SFULL + b], (uint32_t)((j >> 1) & 1));
+                tc5_fence_after();
+                const uint32_t sbuf = base + T5_S + (uint32_t)b * 32768u;
+                {   // row side: D1 += Sh.[Vh|Vl] + Sl.Vh, four k-steps of 8 tile columns
+                    const uint32_t d1 = tmem + 32u * (uint32_t)(e & 1);
+                    const uint64_t dA_h = smem_desc5(sbuf, 512, 512, LAYOUT5_SW128_BASE32B);
+                    const uint64_t dA_l = smem_desc5(sbuf + 16384u, 512, 512, LAYOUT5_SW128_BASE32B);
+                    const uint64_t dB = smem_desc5(base + T5_BT + (uint32_t)b * 4096u, 16, 1024, LAYOUT5_SW128);
+#pragma unroll
+                    for (int ks = 0; ks < 4; ++ks) {
+                        umma5(d1, dA_h + (uint64_t)(ks * 2), dB + (uint64_t)(ks * 2), IDESC_ROW_N32, (j % T5_F != 0 || ks > 0) ? 1u : 0u);
+                        umma5(d1, dA_l + (uint64_t)(ks * 2), dB + (uint64_t)(ks * 2), IDESC_ROW_N16, 1u);
+                    }
+                }
+                if (!diag) {   // column side: D2 = [Sh ; Sl]^T . [Vh|Vl], sixteen k-steps of 8 tile rows
+                    const uint32_t d2 = tmem + 64u + 32u * (uint32_t)b;
+                    const uint64_t dA = smem_desc5(sbuf, 16384, 512, LAYOUT5_SW128_BASE32B);
+                    const uint64_t dB = smem_desc5(base + T5_BC, 16, 1024, LAYOUT5_SW128);
+#pragma unroll
+                    for (int g = 0; g < 16; ++g)
+                        umma5(d2, dA + (uint64_t)((g * 1024) >> 4), dB + (uint64_t)(((g >> 2) * 4096 + (g & 3) * 32) >> 4), IDESC_COL, g > 0 ? 1u : 0u);
+                }
+                umma5_commit(&bars[B5_TDONE + b]);
+            }
+            __syncwarp();
+            mbar5_wait_sleep(&bars[B5_TDONE + b], (uint32_t)((j >> 1) & 1));
+            tc5_fence_after();
+            if (loader) {   // tile j is through: its coordinate stage, S buffer and B stage are free
+                if (tz < it.ntiles) load_z();
+                if (tb < it.ntiles) load_b();
+            }
+            float d[16];
+            if (!diag) {
+                float x[16];
+                const uint32_t ta = tmem + 64u + 32u * (uint32_t)b + ((uint32_t)(qd * 32) << 16);
+                tmem5_ld16(ta, d);
+                tmem5_ld16(ta + 16u, x);
+#pragma unroll
+                for (int c = 0; c < 16; ++c) d[c] += x[c];
+            }
+            tc5_fence_before();
+            __syncwarp();
+            if (lane == 0) mbar5_arrive(&bars[B5_EREAD + b]);
+            if (!diag) {
+                // quadrants 0,1 hold the tf32-part rows of columns 0..15 / 16..31 (lanes 0..15), quadrants 2,3 the remainder rows
+                float* P = reinterpret_cast<float*>(sm + T5_EPI) + (jc & 1) * 1024;
+                if (lane < 16) {
+                    float4* dst = reinterpret_cast<float4*>(P + qd * 256 + lane * 16);
+#pragma unroll
+                    for (int c = 0; c < 4; ++c) dst[c] = make_float4(d[4 * c], d[4 * c + 1], d[4 * c + 2], d[4 * c + 3]);
+                }
+                asm volatile("bar.sync 1, 128;" ::: "memory");
+                const int et = tid - 128, c = et & 15;
+                const long long c0 = it.col0(t);
+#pragma unroll
+                for (int k = 0; k < 4; ++k) {
+                    const int rr = (et >> 4) + 8 * k;      // tile column 0..31 = output row c0 + rr
+                    const float v = P[(rr >> 4) * 256 + (rr & 15) * 16 + c] + P[(2 + (rr >> 4)) * 256 + (rr & 15) * 16 + c];
+                    if (c0 + rr < a.n) atomicAdd(a.acc + (c0 + rr) * T5_N + c, (double)v);
+                }
+                ++jc;
+            }
+        }
+    }
+    tc5_fence_before();
+    __syncthreads();
+    if (warp == 4) {
+        asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, 128;" ::"r"(tmem) : "memory");
+    }
+}
+
+template <int CP, int NP2>
+static int run_sym5(const Sym5Args& a, dim3 grid, cudaStream_t st) {
+    auto kernel = mvm_sym_tc5_kernel<CP, NP2>;
+    cudaError_t e = cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)T5_SMEM_BYTES);
+    if (e != cudaSuccess) return cuda_fail(e, "cudaFuncSetAttribute(mvm_sym_tc5_kernel)");
+    kernel<<<grid, 256, T5_SMEM_BYTES, st>>>(a);
+    note_launch();
+    return cuda_fail(cudaGetLastError(), "mvm_sym_tc5_kernel launch");
+}
+
+// V16 [n][16] -> B operands: per 32 rows one 4096-byte block [16 tf32 parts | 16 remainders][32 rows], K-major SWIZZLE_128B;
+// rows >= n are zero (n_pad = 128 * nblocks rows)
+__global__ void sym5_split_rhs_kernel(const float* __restrict__ v16, long long n, long long n_pad, float* __restrict__ bsplit) {
+    const long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (idx >= n_pad * T5_N) return;
+    const int c = (int)(idx / n_pad);               // consecutive threads = consecutive rows: 128-byte runs in the output
+    const long long row = idx - (long long)c * n_pad;
+    const float v = row < n ? __ldg(v16 + row * T5_N + c) : 0.f;
+    const float h = tf32_hi5(v);
+    unsigned char* blk = reinterpret_cast<unsigned char*>(bsplit) + (row >> 5) * 4096;
+    const uint32_t off = (uint32_t)(c >> 3) * 1024u + sw128_5((uint32_t)(c & 7), (uint32_t)(row & 31));
+    *reinterpret_cast<float*>(blk + off) = h;
+    *reinterpret_cast<float*>(blk + 2048u + off) = v - h;
+}
+
+__global__ void sym5_finalize_kernel(const double* __restrict__ acc, long long n, int t, float* __restrict__ out, int ldo) {
+    const long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (idx >= n * t) return;
+    const long long row = idx / t;
+    const int c = (int)(idx - row * t);
+    out[row * ldo + c] = (float)acc[row * T5_N + c];
+}
+
+int launch_sym_tc5(const float* zp, long long n, int CP, const float* nlc, const float* V16, int t, float* out, int ldo,
+                   int rb_begin, int rb_end, void* workspace, size_t workspace_bytes, cudaStream_t st) {
+    const int nblocks = (int)((n + T5_ROWS - 1) / T5_ROWS);
+    const size_t acc_bytes = ((size_t)n * T5_N * sizeof(double) + 1023) & ~(size_t)1023;
+    const size_t need = acc_bytes + (size_t)nblocks * 16384;
+    if (workspace == nullptr || workspace_bytes < need) {
+        set_error("mvm_sym: workspace %zu bytes < required %zu", workspace_bytes, need);
+        return ERR_WORKSPACE;
+    }
+    double* acc = (double*)workspace;
+    float* bsplit = (float*)((unsigned char*)workspace + acc_bytes);
+    RPGP_CUDA_OK(cudaMemsetAsync(acc, 0, (size_t)n * T5_N * sizeof(double), st));
+    const int nrb = rb_end - rb_begin;
+    if (nrb > 0) {
+        const long long n_pad = (long long)nblocks * T5_ROWS;
+        sym5_split_rhs_kernel<<<(unsigned)((n_pad * T5_N + 255) / 256), 256, 0, st>>>(V16, n, n_pad, bsplit);
+        note_launch();
+        RPGP_CUDA_OK(cudaGetLastError());
+        Sym5Args a;
+        a.z = zp; a.bsplit = bsplit; a.nlc = nlc; a.acc = acc; a.n = n;
+        a.nblocks = nblocks;
+        a.half = nblocks / 2 + 1;
+        a.rb_begin = rb_begin;
+        static const int splits_env = [] { const char* e = getenv("RPGP_SYM_SPLITS"); return e ? atoi(e) : 0; }();
+        long long want = (148LL * 2 * 16 + nrb - 1) / nrb;
+        if (splits_env > 0) want = splits_env;
+        want = std::max<long long>(1, std::min<long long>(want, a.half));
+        a.nsplits = (int)want;
+        dim3 grid((unsigned)nrb, (unsigned)a.nsplits, 1);
+        // polynomial-exp2 pairs (kv_kernels.cuh::exp2_neg_poly2); RPGP_SYM_POLY_PAIRS overrides (tools sweep)
+        static const int np_env = [] { const char* e = getenv("RPGP_SYM_POLY_PAIRS"); return e ? atoi(e) : -1; }();
+        const int np = np_env >= 0 ? np_env : (CP >= 20 ? 2 : (CP >= 16 ? 1 : 0));
+        int rc = ERR_UNSUPPORTED;
+#define RPGP_SYM5_CASE(CPv, NPv) if (CP == CPv && np == NPv) rc = run_sym5<CPv, NPv>(a, grid, st);
+        RPGP_SYM5_CASE(4, 0) RPGP_SYM5_CASE(8, 0) RPGP_SYM5_CASE(12, 0) RPGP_SYM5_CASE(16, 0) RPGP_SYM5_CASE(16, 1)
+        RPGP_SYM5_CASE(20, 0) RPGP_SYM5_CASE(20, 1) RPGP_SYM5_CASE(20, 2) RPGP_SYM5_CASE(20, 3) RPGP_SYM5_CASE(24, 0) RPGP_SYM5_CASE(24, 2)
+        RPGP_SYM5_CASE(28, 0) RPGP_SYM5_CASE(28, 2) RPGP_SYM5_CASE(32, 0) RPGP_SYM5_CASE(32, 2)
+#undef RPGP_SYM5_CASE
+        if (rc == ERR_UNSUPPORTED) set_error("mvm_sym: no kernel for CP=%d poly pairs=%d (compiled: 0 for every CP, 1 for CP 16/20, 2 for CP >= 20)", CP, np);
+        if (rc) return rc;
+    }
+    const long long total = n * t;
+    sym5_finalize_kernel<<<(unsigned)((total + 255) / 256), 256, 0, st>>>(acc, n, t, out, ldo);
+    note_launch();
+    return cuda_fail(cudaGetLastError(), "sym5_finalize_kernel");
+}
+
+}  // namespace rpgp
