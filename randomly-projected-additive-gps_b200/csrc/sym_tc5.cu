@@ -14,8 +14,10 @@
 // into Kahan-compensated FP32 registers; the column side is read back per tile by four epilogue warps (TMEM lane quadrants 0..3),
 // combined through shared memory and added to FP64 accumulators with coalesced atomics.
 //
-// CTA = 256 threads: warps 0-3 arithmetic (setmaxnreg.inc), warps 4-7 epilogue (setmaxnreg.dec); lane 0 of warp 4 also issues the
-// MMAs of a tile, lane 0 of warp 5 also issues the bulk copies (all buffers are released by the tile's tcgen05.commit).
+// CTA = 128*HALVES arithmetic threads (setmaxnreg.inc) + 4 epilogue warps (setmaxnreg.dec).  HALVES = 1: thread = row, all 32
+// columns of a tile; HALVES = 2: two threads per row, 16 columns each -> 16 arithmetic warps per SM at <= 96 registers, which
+// hides the MUFU / FADD2 latencies that two warps per scheduler cannot.  Lane 0 of the first epilogue warp also issues the MMAs
+// of a tile, lane 0 of the second one the bulk copies (all buffers are released by the tile's tcgen05.commit).
 #include <algorithm>
 #include <cstdlib>
 
@@ -32,6 +34,13 @@ constexpr int T5_BN = 32;        // columns per tile
 constexpr int T5_N = 16;         // padded right-hand sides
 constexpr int T5_F = 4;          // tiles accumulated in TMEM per row-side epoch (K = 128 per flush, like the column side)
 constexpr int T5_ZST = 3;        // coordinate-tile stages
+#ifndef T5_QUNROLL
+#define T5_QUNROLL 1
+#endif
+#ifndef T5_DIAG
+#define T5_DIAG 0                // diagnostic builds only (tools/sym5_variants.sh): 1 no column-side atomics, 2 no column-side MMAs, 4 no row-side MMAs
+#endif
+constexpr int T5_QU = T5_QUNROLL;   // unroll factor of the 4-column groups inside a tile
 #ifndef T5_REGS_ARITH
 #define T5_REGS_ARITH 184
 #endif
@@ -110,6 +119,15 @@ __device__ __forceinline__ void tmem5_ld16(uint32_t taddr, float* v) {
 #pragma unroll
     for (int q = 0; q < 16; ++q) v[q] = __uint_as_float(r[q]);
 }
+__device__ __forceinline__ void tmem5_ld8(uint32_t taddr, float* v) {
+    uint32_t r[8];
+    asm volatile("tcgen05.ld.sync.aligned.32x32b.x8.b32 {%0,%1,%2,%3,%4,%5,%6,%7}, [%8];"
+                 : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7])
+                 : "r"(taddr));
+    asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+#pragma unroll
+    for (int q = 0; q < 8; ++q) v[q] = __uint_as_float(r[q]);
+}
 __device__ __forceinline__ float tf32_hi5(float x) { return __uint_as_float(__float_as_uint(x) & 0xFFFFE000u); }
 __host__ __device__ __forceinline__ uint32_t sw128_5(uint32_t row, uint32_t kk) {
     return row * 128u + ((((kk >> 2) ^ (row & 7u)) << 4) | ((kk & 3u) << 2));
@@ -138,8 +156,11 @@ struct Tile5Iter {
 
 }  // namespace
 
-template <int CP, int NP2>
-__global__ void __launch_bounds__(256, 2) mvm_sym_tc5_kernel(const Sym5Args a) {
+template <int CP, int NP2, int HALVES>
+__global__ void __launch_bounds__(128 * HALVES + 128, 2) mvm_sym_tc5_kernel(const Sym5Args a) {
+    constexpr int AW = 4 * HALVES;                 // arithmetic warps
+    constexpr int FC = T5_N / HALVES;              // right-hand-side columns folded by one arithmetic warp
+    constexpr int REGS_ARITH = HALVES == 1 ? T5_REGS_ARITH : 96, REGS_HELP = HALVES == 1 ? T5_REGS_HELP : 48;
     extern __shared__ unsigned char smem_raw[];
     const uint32_t base = (smem_u32(smem_raw) + 1023u) & ~1023u;
     unsigned char* sm = smem_raw + (base - smem_u32(smem_raw));
@@ -162,15 +183,15 @@ __global__ void __launch_bounds__(256, 2) mvm_sym_tc5_kernel(const Sym5Args a) {
 #pragma unroll
         for (int b = 0; b < 2; ++b) {
             mbar_init(&bars[B5_BFULL + b], 1);
-            mbar_init(&bars[B5_SFULL + b], 4);
+            mbar_init(&bars[B5_SFULL + b], AW);
             mbar_init(&bars[B5_TDONE + b], 1);
             mbar_init(&bars[B5_EREAD + b], 4);
-            mbar_init(&bars[B5_D1EMPTY + b], 4);
+            mbar_init(&bars[B5_D1EMPTY + b], AW);
         }
         mbar_init(&bars[B5_BCFULL], 1);
         mbar_fence_init();
     }
-    if (warp == 4) {
+    if (warp == AW) {
         asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], 128;" ::"r"(smem_u32(tmem_slot)) : "memory");
         asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
     }
@@ -179,28 +200,30 @@ __global__ void __launch_bounds__(256, 2) mvm_sym_tc5_kernel(const Sym5Args a) {
     tc5_fence_after();
     const uint32_t tmem = *tmem_slot;   // D1[epoch & 1] (row side, 128 lanes x 32 columns) at column 32*(epoch&1); D2[b] at 64 + 32*b
 
-    if (warp < 4) {
+    if (warp < AW) {
         // =========================================== arithmetic warps ===================================================
-        asm volatile("setmaxnreg.inc.sync.aligned.u32 %0;" ::"n"(T5_REGS_ARITH));
-        const long long row = (long long)it.I * T5_ROWS + tid;
+        asm volatile("setmaxnreg.inc.sync.aligned.u32 %0;" ::"n"(REGS_ARITH));
+        const int rtid = tid & (T5_ROWS - 1), half = tid >> 7;     // row in the block; which part of the tile's columns
+        const long long row = (long long)it.I * T5_ROWS + rtid;
         const bool valid = row < a.n;
         RowCoords<CP, 1, CP> r;
         load_row_coords<CP, 1, CP>(r, a.z + row * CP, valid, a.nlc);
-        f32x2 acc[T5_N / 2], comp[T5_N / 2];
+        f32x2 acc[FC / 2], comp[FC / 2];
 #pragma unroll
-        for (int q = 0; q < T5_N / 2; ++q) { acc[q] = 0ull; comp[q] = 0ull; }
+        for (int q = 0; q < FC / 2; ++q) { acc[q] = 0ull; comp[q] = 0ull; }
 
-        // fold one closed epoch of the row-side accumulator (this warp's 32 TMEM lanes = its own rows) into the running total
+        // fold one closed epoch of the row-side accumulator (TMEM lanes of this warp's quadrant = its rows; with two threads per
+        // row each takes half of the right-hand sides) into the running total
         auto fold_epoch = [&](int e) {
-            float d[16], x[16];
-            const uint32_t ta = tmem + 32u * (uint32_t)(e & 1) + ((uint32_t)(warp * 32) << 16);
-            tmem5_ld16(ta, d);          // Sh.Vh + Sl.Vh
-            tmem5_ld16(ta + 16u, x);    // Sh.Vl
+            float d[FC], x[FC];
+            const uint32_t ta = tmem + 32u * (uint32_t)(e & 1) + (uint32_t)(half * FC) + ((uint32_t)((warp & 3) * 32) << 16);
+            if constexpr (FC == 16) { tmem5_ld16(ta, d); tmem5_ld16(ta + 16u, x); }    // Sh.Vh + Sl.Vh | Sh.Vl
+            else { tmem5_ld8(ta, d); tmem5_ld8(ta + 16u, x); }
             tc5_fence_before();
             __syncwarp();
             if (lane == 0) mbar5_arrive(&bars[B5_D1EMPTY + (e & 1)]);
 #pragma unroll
-            for (int q = 0; q < T5_N / 2; ++q) {
+            for (int q = 0; q < FC / 2; ++q) {
                 const f32x2 y = sub2(pack2(d[2 * q] + x[2 * q], d[2 * q + 1] + x[2 * q + 1]), comp[q]);
                 const f32x2 tsum = add2(acc[q], y);
                 comp[q] = sub2(sub2(tsum, acc[q]), y);
@@ -223,8 +246,8 @@ __global__ void __launch_bounds__(256, 2) mvm_sym_tc5_kernel(const Sym5Args a) {
             unsigned char* sc = sm + T5_S + (uint32_t)b * 32768u;
             auto tile_body = [&](auto full_tile) {
                 constexpr bool FULL = decltype(full_tile)::value;
-#pragma unroll 1
-                for (int q = 0; q < T5_BN / 4; ++q) {
+#pragma unroll T5_QU
+                for (int q = half * (T5_BN / 4 / HALVES); q < (half + 1) * (T5_BN / 4 / HALVES); ++q) {
                     float sv[4];
 #pragma unroll
                     for (int e = 0; e < 4; ++e) {
@@ -236,7 +259,7 @@ __global__ void __launch_bounds__(256, 2) mvm_sym_tc5_kernel(const Sym5Args a) {
                     float4 h, l;
                     h.x = tf32_hi5(sv[0]); h.y = tf32_hi5(sv[1]); h.z = tf32_hi5(sv[2]); h.w = tf32_hi5(sv[3]);
                     l.x = sv[0] - h.x; l.y = sv[1] - h.y; l.z = sv[2] - h.z; l.w = sv[3] - h.w;
-                    const uint32_t off = (uint32_t)tid * 128u + (((((uint32_t)q >> 1) ^ ((uint32_t)tid & 3u)) << 5) | (((uint32_t)q & 1u) << 4));
+                    const uint32_t off = (uint32_t)rtid * 128u + (((((uint32_t)q >> 1) ^ ((uint32_t)rtid & 3u)) << 5) | (((uint32_t)q & 1u) << 4));
                     *reinterpret_cast<float4*>(sc + off) = h;
                     *reinterpret_cast<float4*>(sc + 16384u + off) = l;
                 }
@@ -252,9 +275,9 @@ __global__ void __launch_bounds__(256, 2) mvm_sym_tc5_kernel(const Sym5Args a) {
             const int epochs = (j + T5_F - 1) / T5_F;
             while (folded < epochs) fold_epoch(folded++);
             if (valid) {
-                double* dst = a.acc + row * T5_N;
+                double* dst = a.acc + row * T5_N + half * FC;
 #pragma unroll
-                for (int q = 0; q < T5_N / 2; ++q) {
+                for (int q = 0; q < FC / 2; ++q) {
                     float x, y;
                     unpack2(acc[q], x, y);
                     atomicAdd(dst + 2 * q, (double)x);
@@ -264,9 +287,9 @@ __global__ void __launch_bounds__(256, 2) mvm_sym_tc5_kernel(const Sym5Args a) {
         }
     } else {
         // =========================================== epilogue warps (+ MMA issue, + bulk copies) ========================
-        asm volatile("setmaxnreg.dec.sync.aligned.u32 %0;" ::"n"(T5_REGS_HELP));
-        const int qd = warp - 4;                                   // TMEM lane quadrant
-        const bool issuer = (warp == 4 && lane == 0), loader = (warp == 5 && lane == 0);
+        asm volatile("setmaxnreg.dec.sync.aligned.u32 %0;" ::"n"(REGS_HELP));
+        const int qd = warp - AW;                                  // TMEM lane quadrant (AW is a multiple of 4)
+        const bool issuer = (qd == 0 && lane == 0), loader = (qd == 1 && lane == 0);
         constexpr uint32_t IDESC_ROW_N32 = idesc5_tf32(128, 2 * T5_N, 0, 0), IDESC_ROW_N16 = idesc5_tf32(128, T5_N, 0, 0);
         constexpr uint32_t IDESC_COL = idesc5_tf32(64, 2 * T5_N, 1, 0);
         const unsigned char* bsplit = reinterpret_cast<const unsigned char*>(a.bsplit);
@@ -310,7 +333,7 @@ __global__ void __launch_bounds__(256, 2) mvm_sym_tc5_kernel(const Sym5Args a) {
                 mbar5_wait_sleep(&bars[B5_SFULL + b], (uint32_t)((j >> 1) & 1));
                 tc5_fence_after();
                 const uint32_t sbuf = base + T5_S + (uint32_t)b * 32768u;
-                {   // row side: D1 += Sh.[Vh|Vl] + Sl.Vh, four k-steps of 8 tile columns
+                if (!(T5_DIAG & 4)) {   // row side: D1 += Sh.[Vh|Vl] + Sl.Vh, four k-steps of 8 tile columns
                     const uint32_t d1 = tmem + 32u * (uint32_t)(e & 1);
                     const uint64_t dA_h = smem_desc5(sbuf, 512, 512, LAYOUT5_SW128_BASE32B);
                     const uint64_t dA_l = smem_desc5(sbuf + 16384u, 512, 512, LAYOUT5_SW128_BASE32B);
@@ -321,7 +344,7 @@ __global__ void __launch_bounds__(256, 2) mvm_sym_tc5_kernel(const Sym5Args a) {
                         umma5(d1, dA_l + (uint64_t)(ks * 2), dB + (uint64_t)(ks * 2), IDESC_ROW_N16, 1u);
                     }
                 }
-                if (!diag) {   // column side: D2 = [Sh ; Sl]^T . [Vh|Vl], sixteen k-steps of 8 tile rows
+                if (!diag && !(T5_DIAG & 2)) {   // column side: D2 = [Sh ; Sl]^T . [Vh|Vl], sixteen k-steps of 8 tile rows
                     const uint32_t d2 = tmem + 64u + 32u * (uint32_t)b;
                     const uint64_t dA = smem_desc5(sbuf, 16384, 512, LAYOUT5_SW128_BASE32B);
                     const uint64_t dB = smem_desc5(base + T5_BC, 16, 1024, LAYOUT5_SW128);
@@ -338,34 +361,34 @@ __global__ void __launch_bounds__(256, 2) mvm_sym_tc5_kernel(const Sym5Args a) {
                 if (tz < it.ntiles) load_z();
                 if (tb < it.ntiles) load_b();
             }
-            float d[16];
+            // quadrants 0,1 hold the tf32-part rows of columns 0..15 / 16..31 (lanes 0..15), quadrants 2,3 the remainder rows
+            float* P = reinterpret_cast<float*>(sm + T5_EPI) + (jc & 1) * 1024;
             if (!diag) {
-                float x[16];
                 const uint32_t ta = tmem + 64u + 32u * (uint32_t)b + ((uint32_t)(qd * 32) << 16);
-                tmem5_ld16(ta, d);
-                tmem5_ld16(ta + 16u, x);
 #pragma unroll
-                for (int c = 0; c < 16; ++c) d[c] += x[c];
+                for (int ch = 0; ch < 2; ++ch) {   // 8 right-hand sides at a time: [Vh part | Vl part] summed
+                    float d[8], x[8];
+                    tmem5_ld8(ta + 8u * ch, d);
+                    tmem5_ld8(ta + 16u + 8u * ch, x);
+                    if (lane < 16) {
+                        float4* dst = reinterpret_cast<float4*>(P + qd * 256 + lane * 16 + 8 * ch);
+                        dst[0] = make_float4(d[0] + x[0], d[1] + x[1], d[2] + x[2], d[3] + x[3]);
+                        dst[1] = make_float4(d[4] + x[4], d[5] + x[5], d[6] + x[6], d[7] + x[7]);
+                    }
+                }
             }
             tc5_fence_before();
             __syncwarp();
             if (lane == 0) mbar5_arrive(&bars[B5_EREAD + b]);
             if (!diag) {
-                // quadrants 0,1 hold the tf32-part rows of columns 0..15 / 16..31 (lanes 0..15), quadrants 2,3 the remainder rows
-                float* P = reinterpret_cast<float*>(sm + T5_EPI) + (jc & 1) * 1024;
-                if (lane < 16) {
-                    float4* dst = reinterpret_cast<float4*>(P + qd * 256 + lane * 16);
-#pragma unroll
-                    for (int c = 0; c < 4; ++c) dst[c] = make_float4(d[4 * c], d[4 * c + 1], d[4 * c + 2], d[4 * c + 3]);
-                }
                 asm volatile("bar.sync 1, 128;" ::: "memory");
-                const int et = tid - 128, c = et & 15;
+                const int et = tid - 32 * AW, c = et & 15;
                 const long long c0 = it.col0(t);
 #pragma unroll
                 for (int k = 0; k < 4; ++k) {
                     const int rr = (et >> 4) + 8 * k;      // tile column 0..31 = output row c0 + rr
                     const float v = P[(rr >> 4) * 256 + (rr & 15) * 16 + c] + P[(2 + (rr >> 4)) * 256 + (rr & 15) * 16 + c];
-                    if (c0 + rr < a.n) atomicAdd(a.acc + (c0 + rr) * T5_N + c, (double)v);
+                    if (c0 + rr < a.n && !(T5_DIAG & 1)) atomicAdd(a.acc + (c0 + rr) * T5_N + c, (double)v);
                 }
                 ++jc;
             }
@@ -373,17 +396,17 @@ __global__ void __launch_bounds__(256, 2) mvm_sym_tc5_kernel(const Sym5Args a) {
     }
     tc5_fence_before();
     __syncthreads();
-    if (warp == 4) {
+    if (warp == AW) {
         asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, 128;" ::"r"(tmem) : "memory");
     }
 }
 
-template <int CP, int NP2>
+template <int CP, int NP2, int HALVES>
 static int run_sym5(const Sym5Args& a, dim3 grid, cudaStream_t st) {
-    auto kernel = mvm_sym_tc5_kernel<CP, NP2>;
+    auto kernel = mvm_sym_tc5_kernel<CP, NP2, HALVES>;
     cudaError_t e = cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)T5_SMEM_BYTES);
     if (e != cudaSuccess) return cuda_fail(e, "cudaFuncSetAttribute(mvm_sym_tc5_kernel)");
-    kernel<<<grid, 256, T5_SMEM_BYTES, st>>>(a);
+    kernel<<<grid, 128 * HALVES + 128, T5_SMEM_BYTES, st>>>(a);
     note_launch();
     return cuda_fail(cudaGetLastError(), "mvm_sym_tc5_kernel launch");
 }
@@ -444,7 +467,14 @@ int launch_sym_tc5(const float* zp, long long n, int CP, const float* nlc, const
         static const int np_env = [] { const char* e = getenv("RPGP_SYM_POLY_PAIRS"); return e ? atoi(e) : -1; }();
         const int np = np_env >= 0 ? np_env : (CP >= 20 ? 2 : (CP >= 16 ? 1 : 0));
         int rc = ERR_UNSUPPORTED;
-#define RPGP_SYM5_CASE(CPv, NPv) if (CP == CPv && np == NPv) rc = run_sym5<CPv, NPv>(a, grid, st);
+        // two threads per row where the row's coordinates leave room in 96 registers; RPGP_SYM_HALVES overrides (tools sweep)
+        static const int halves_env = [] { const char* e = getenv("RPGP_SYM_HALVES"); return e ? atoi(e) : 0; }();
+        const int halves = halves_env ? halves_env : (CP <= 24 ? 2 : 1);
+#define RPGP_SYM5_CASE(CPv, NPv)                                                                                       \
+        if (CP == CPv && np == NPv) {                                                                                  \
+            if constexpr (CPv <= 24) rc = halves == 2 ? run_sym5<CPv, NPv, 2>(a, grid, st) : run_sym5<CPv, NPv, 1>(a, grid, st); \
+            else rc = run_sym5<CPv, NPv, 1>(a, grid, st);                                                              \
+        }
         RPGP_SYM5_CASE(4, 0) RPGP_SYM5_CASE(8, 0) RPGP_SYM5_CASE(12, 0) RPGP_SYM5_CASE(16, 0) RPGP_SYM5_CASE(16, 1)
         RPGP_SYM5_CASE(20, 0) RPGP_SYM5_CASE(20, 1) RPGP_SYM5_CASE(20, 2) RPGP_SYM5_CASE(20, 3) RPGP_SYM5_CASE(24, 0) RPGP_SYM5_CASE(24, 2)
         RPGP_SYM5_CASE(28, 0) RPGP_SYM5_CASE(28, 2) RPGP_SYM5_CASE(32, 0) RPGP_SYM5_CASE(32, 2)
