@@ -316,6 +316,16 @@ def run_ours(args, w):
     ex2_alg = float(m_rows) * n * J
     fp32_alg = float(m_rows) * n * ((3 * J + t) if K == 1 else (J * (2 * K + 1) + t))
     ach = ex2_alg / (kernel_ms * 1e-3)
+    TPb = _lib.padded_rhs(lay, min(t, 16), False)
+    # exponential pairs the kernels hand to the FMA-pipe polynomial (csrc/dispatch.cuh default_poly_pairs, sym_tc5.cu launcher)
+    if K != 1:
+        np2 = 0
+    elif use_sym:
+        np2 = int(os.environ.get("RPGP_SYM_POLY_PAIRS", 2 if lay.CP >= 20 else (1 if lay.CP >= 16 else 0)))
+    else:
+        np2 = int(os.environ.get("RPGP_POLY_PAIRS", 0 if TPb > 16 else (3 if lay.CP >= 28 else 2 if lay.CP >= 16 else 1 if lay.CP >= 8 else 0)))
+    evals = (float(n) * n / 2 / world) if use_sym else float(m_rows) * n          # kernel values actually formed by this rank
+    xu_ex2 = evals * (groups - 2 * np2)
     hbm_peak = None
     try:
         hbm_peak = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))["hbm_gbs"]
@@ -331,13 +341,15 @@ def run_ours(args, w):
         "bound": "mufu", "achieved": ach / 1e12, "peak": mufu_peak / 1e12, "unit": "Tex2/s", "frac": ach / mufu_peak,
         "peak_source": "measured live: rpgp_measure_peaks mufu_ex2 %.2f/clk/SM x %d SMs x %.0f MHz"
                        % (peaks["mufu_ex2"]["mufu_per_clk_sm"], sms, peaks["mufu_ex2"]["mhz"]),
-        "kernel": ("mvm_sym_tc3_kernel<CP=%d> (symmetric: each kernel value evaluated once, column side on tcgen05)" % lay.CP) if use_sym
-                  else "mvm_fwd_kernel<CP=%d,TP=%d,KP=%d,G=%d>" % (lay.CP, _lib.padded_rhs(lay, min(t, 16), False), lay.KP, lay.G),
-        "note": "achieved counts the ALGORITHMIC exponentials of SURVEY 8(d) (m*n*J per product); the kernel evaluates fewer on the "
-                "XU pipe (symmetry halves them, ~20% more go to an FMA-pipe polynomial), so frac can exceed 1" if use_sym else
-                "achieved counts the algorithmic exponentials m*n*J; ~20% of them are evaluated by an FMA-pipe polynomial, so frac can exceed 1",
+        "kernel": ("mvm_sym_tc5_kernel<CP=%d,NP2=%d> (symmetric: each kernel value evaluated once; S.V and S^T.V both on tcgen05 "
+                   "kind::tf32, 3xTF32 split)" % (lay.CP, np2)) if use_sym
+                  else "mvm_fwd_kernel<CP=%d,TP=%d,KP=%d,G=%d,NP2=%d>" % (lay.CP, TPb, lay.KP, lay.G, np2),
+        "note": "achieved counts the ALGORITHMIC exponentials of SURVEY 8(d) (m*n*J per product), so frac can exceed 1: "
+                + ("symmetry halves the evaluations and " if use_sym else "")
+                + "%d of every %d exponentials are evaluated by an FMA-pipe polynomial; xu_frac is the XU (MUFU) pipe's own utilisation "
+                  "by the MUFU.EX2 actually issued" % (2 * np2, groups),
         "kernel_ms": kernel_ms, "kernel_share_of_step": kernel_ms / ms_per_step,
-        "algorithmic_ex2_per_launch": ex2_alg, "issued_ex2_per_launch": (float(n) * n * groups / 2 / world) if use_sym else float(m_rows) * n * groups,
+        "algorithmic_ex2_per_launch": ex2_alg, "xu_ex2_per_launch": xu_ex2, "xu_frac": xu_ex2 / (kernel_ms * 1e-3) / mufu_peak,
         "fp32_frac": (fp32_alg / (kernel_ms * 1e-3)) / fp32_peak, "fp32_peak_Tlaneops": fp32_peak / 1e12,
         "traffic": traffic,
         "hbm": {"algorithmic_bytes_per_launch": alg_bytes, "achieved_GBps": alg_bytes / (kernel_ms * 1e-3) / 1e9,
@@ -358,7 +370,9 @@ def run_ours(args, w):
         "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms_per_step, "higher_is_better": True,
         "scaling": "strong", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
         "config": {"workload": w["desc"], "n": n, "d": d, "J": J, "K": K, "t": t, "noise": noise,
-                   "parallelism": "rows of K over %d rank(s), NCCL all-gather per CG iteration" % world,
+                   "parallelism": ("unique 128-row block pairs of the symmetric K over %d rank(s), NCCL all-reduce(sum) of the partial "
+                                   "products per CG iteration" if use_sym else
+                                   "rows of K over %d rank(s), NCCL all-gather per CG iteration") % world,
                    "l2": "inputs larger than L2 (Z^ %.0f MB, V %.0f MB)" % (n * lay.nchunks * lay.CP * 4 / 1e6, n * t * 4 / 1e6)
                    if n * lay.nchunks * lay.CP * 4 > 126e6 else "inputs fit in L2 (reused every step by design: Z^ is read n/256 times per launch)"},
         "cg_iters_per_s": 1e3 / ms_per_step, "pairs_per_s": value / J,
