@@ -206,7 +206,7 @@ def run_ours(args, w):
     del Xd
     nlc = _lib.pack_log2c(c.to(dev), lay)
 
-    use_sym = (not args.no_sym) and _lib.mvm_sym_supported(lay, t) and lay.nchunks == 1
+    use_sym = (not args.no_sym) and _lib.mvm_sym_supported(lay, t)
     nblocks128 = (n + 127) // 128
     sper = (nblocks128 + world - 1) // world
     sb0, sb1 = min(nblocks128, rank * sper), min(nblocks128, (rank + 1) * sper)

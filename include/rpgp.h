@@ -90,7 +90,8 @@ int rpgp_mvm_fwd_f32(const float* z1p, int64_t m, int64_t z1_stride, const float
 
 /* symmetric forward K(Z,Z).V on the tensor cores ---------------------------------------------------------------------
  * Every kernel value is evaluated once and used for both out[i] and out[i'] (tcgen05, 3xTF32 split, FP64 global
- * accumulation); K == 1, J <= 32, t <= 16 (rpgp_mvm_sym_supported).  Vp16: [n][16] zero-padded right-hand sides.
+ * accumulation); any layout of rpgp_plan_layout (K >= 1; coordinate chunks are summed), t <= 16 per call
+ * (rpgp_mvm_sym_supported).  zp: [nchunks][n][CP].  Vp16: [n][16] zero-padded right-hand sides.
  * Row blocks are 128 rows; a launch handles the unique block pairs owned by row blocks [row_block_begin, row_block_end)
  * and writes their contributions to ALL n rows of out -- with the full range [0, ceil(n/128)) out is K.V, with a
  * sub-range (one rank of a multi-GPU job) the outputs of the ranks must be summed (all-reduce).

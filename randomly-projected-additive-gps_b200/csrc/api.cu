@@ -198,14 +198,14 @@ size_t rpgp_mvm_sym_workspace_bytes(int64_t n, const rpgp_layout* lay) {
 }
 
 int rpgp_mvm_sym_supported(const rpgp_layout* lay, int t) {
-    return lay && lay->K == 1 && lay->nchunks == 1 && t >= 1 && t <= 16;
+    return lay && check_layout(lay) == OK && t >= 1 && t <= 16;
 }
 
 int rpgp_mvm_sym_f32(const float* zp, int64_t n, const rpgp_layout* lay, const float* neg_log2c, const float* Vp16, int t,
                      float* out, int ldo, int row_block_begin, int row_block_end, void* workspace, size_t workspace_bytes,
                      void* stream) {
     if (int rc = check_layout(lay)) return rc;
-    RPGP_REQUIRE(rpgp_mvm_sym_supported(lay, t), "mvm_sym: needs K == 1, J <= 32 and t <= 16 (got K=%d, chunks=%d, t=%d)", lay->K, lay->nchunks, t);
+    RPGP_REQUIRE(rpgp_mvm_sym_supported(lay, t), "mvm_sym: needs 1 <= t <= 16 right-hand sides per call (got t=%d)", t);
     RPGP_REQUIRE(n >= 1 && ldo >= t, "mvm_sym: n=%lld ldo=%d", (long long)n, ldo);
     RPGP_REQUIRE(zp && neg_log2c && Vp16 && out, "mvm_sym: NULL pointer");
     RPGP_REQUIRE(aligned16(zp) && aligned16(Vp16), "mvm_sym: operands must be 16-byte aligned");
@@ -214,10 +214,10 @@ int rpgp_mvm_sym_f32(const float* zp, int64_t n, const rpgp_layout* lay, const f
                  "mvm_sym: row block range [%d, %d) outside [0, %d]", row_block_begin, row_block_end, nblocks);
     // RPGP_SYM_KERNEL=3 selects the earlier variant (row side in registers) for A/B runs
     static const int variant = [] { const char* e = getenv("RPGP_SYM_KERNEL"); return e ? atoi(e) : 5; }();
-    if (variant == 3)
+    if (variant == 3 && lay->K == 1 && lay->nchunks == 1)
         return launch_sym_tc3(zp, n, lay->CP, neg_log2c, Vp16, t, out, ldo, row_block_begin, row_block_end, workspace,
                               workspace_bytes, (cudaStream_t)stream);
-    return launch_sym_tc5(zp, n, lay->CP, neg_log2c, Vp16, t, out, ldo, row_block_begin, row_block_end, workspace,
+    return launch_sym_tc5(zp, n, *reinterpret_cast<const Layout*>(lay), neg_log2c, Vp16, t, out, ldo, row_block_begin, row_block_end, workspace,
                           workspace_bytes, (cudaStream_t)stream);
 }
 

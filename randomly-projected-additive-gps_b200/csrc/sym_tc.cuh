@@ -8,7 +8,8 @@ inline size_t sym_workspace_bytes(long long n) {
     return (((size_t)n * 16 * sizeof(double) + 1023) & ~(size_t)1023) + (size_t)((n + 127) / 128) * 16384 + 512;
 }
 // both uses of every kernel value on the tensor cores (sym_tc5.cu): the default
-int launch_sym_tc5(const float* zp, long long n, int CP, const float* nlc, const float* V16, int t, float* out, int ldo,
+struct Layout;
+int launch_sym_tc5(const float* zp, long long n, const Layout& lay, const float* nlc, const float* V16, int t, float* out, int ldo,
                    int rb_begin, int rb_end, void* workspace, size_t workspace_bytes, cudaStream_t st);
 // warp-specialised variant (sym_tc3.cu): row side in registers, column side on the tensor cores issued by dedicated warps
 int launch_sym_tc3(const float* zp, long long n, int CP, const float* nlc, const float* V16, int t, float* out, int ldo,

@@ -22,6 +22,7 @@
 #include <cstdlib>
 
 #include "aux_kernels.cuh"
+#include "dispatch.cuh"
 #include "kv_kernels.cuh"
 #include "sym_tc.cuh"
 
@@ -134,13 +135,14 @@ __host__ __device__ __forceinline__ uint32_t sw128_5(uint32_t row, uint32_t kk) 
 }
 
 struct Sym5Args {
-    const float* z;        // [n][CP]
+    const float* z;        // [nchunks][n][CP]  (blockIdx.z = coordinate chunk; the chunks' kernel values add up, so do their products)
     const float* bsplit;   // [nblocks*4][4096 B] pre-split right-hand sides (B operands)
-    const float* nlc;      // [CP]
+    const float* nlc;      // [nchunks][CP or G]
     double* acc;           // [n][16] FP64 accumulators (zeroed by the launcher)
     long long n;
     int nblocks, half, nsplits, rb_begin;
 };
+
 
 // tile enumeration shared by all roles: offsets k in [k_begin, k_end), four 32-column tiles per 128-column block
 struct Tile5Iter {
@@ -156,8 +158,9 @@ struct Tile5Iter {
 
 }  // namespace
 
-template <int CP, int NP2, int HALVES>
+template <int CP, int KP, int G, int NP2, int HALVES>
 __global__ void __launch_bounds__(128 * HALVES + 128, 2) mvm_sym_tc5_kernel(const Sym5Args a) {
+    constexpr int GP = (KP == 1) ? CP : G;         // -log2c entries per chunk
     constexpr int AW = 4 * HALVES;                 // arithmetic warps
     constexpr int FC = T5_N / HALVES;              // right-hand-side columns folded by one arithmetic warp
     constexpr int REGS_ARITH = HALVES == 1 ? T5_REGS_ARITH : 96, REGS_HELP = HALVES == 1 ? T5_REGS_HELP : 48;
@@ -168,6 +171,7 @@ __global__ void __launch_bounds__(128 * HALVES + 128, 2) mvm_sym_tc5_kernel(cons
     uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(sm + T5_BAR + 192);
 
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+    const float* zc = a.z + (long long)blockIdx.z * a.n * CP;      // this CTA's coordinate chunk
     Tile5Iter it;
     it.I = a.rb_begin + blockIdx.x;
     it.B = a.nblocks;
@@ -206,8 +210,8 @@ __global__ void __launch_bounds__(128 * HALVES + 128, 2) mvm_sym_tc5_kernel(cons
         const int rtid = tid & (T5_ROWS - 1), half = tid >> 7;     // row in the block; which part of the tile's columns
         const long long row = (long long)it.I * T5_ROWS + rtid;
         const bool valid = row < a.n;
-        RowCoords<CP, 1, CP> r;
-        load_row_coords<CP, 1, CP>(r, a.z + row * CP, valid, a.nlc);
+        RowCoords<CP, KP, G> r;
+        load_row_coords<CP, KP, G>(r, zc + row * CP, valid, a.nlc + (int)blockIdx.z * GP);
         f32x2 acc[FC / 2], comp[FC / 2];
 #pragma unroll
         for (int q = 0; q < FC / 2; ++q) { acc[q] = 0ull; comp[q] = 0ull; }
@@ -252,7 +256,7 @@ __global__ void __launch_bounds__(128 * HALVES + 128, 2) mvm_sym_tc5_kernel(cons
 #pragma unroll
                     for (int e = 0; e < 4; ++e) {
                         const int c = 4 * q + e;
-                        const float val = pair_kernel_value<CP, 1, CP, NP2>(r, zt + c * CP);
+                        const float val = pair_kernel_value<CP, KP, G, NP2>(r, zt + c * CP);
                         sv[e] = (FULL || c < cols) ? val : 0.f;      // columns behind a partial tile hold stale bytes
                     }
                     // split, SWIZZLE_128B_BASE32B (32-byte chunks ^ row % 4), row-local stores
@@ -301,7 +305,7 @@ __global__ void __launch_bounds__(128 * HALVES + 128, 2) mvm_sym_tc5_kernel(cons
             const uint32_t cols = (uint32_t)min((long long)T5_BN, a.n - c0);
             const int zs = jz % T5_ZST;
             mbar_expect_tx(&bars[B5_ZFULL + zs], cols * CP * (uint32_t)sizeof(float));
-            bulk_g2s(sm + T5_Z + (uint32_t)zs * T5_BN * CP * 4u, a.z + c0 * CP, cols * CP * (uint32_t)sizeof(float), &bars[B5_ZFULL + zs]);
+            bulk_g2s(sm + T5_Z + (uint32_t)zs * T5_BN * CP * 4u, zc + c0 * CP, cols * CP * (uint32_t)sizeof(float), &bars[B5_ZFULL + zs]);
             tz = it.next_live(tz + 1);
             ++jz;
         };
@@ -401,9 +405,9 @@ __global__ void __launch_bounds__(128 * HALVES + 128, 2) mvm_sym_tc5_kernel(cons
     }
 }
 
-template <int CP, int NP2, int HALVES>
+template <int CP, int KP, int G, int NP2, int HALVES>
 static int run_sym5(const Sym5Args& a, dim3 grid, cudaStream_t st) {
-    auto kernel = mvm_sym_tc5_kernel<CP, NP2, HALVES>;
+    auto kernel = mvm_sym_tc5_kernel<CP, KP, G, NP2, HALVES>;
     cudaError_t e = cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)T5_SMEM_BYTES);
     if (e != cudaSuccess) return cuda_fail(e, "cudaFuncSetAttribute(mvm_sym_tc5_kernel)");
     kernel<<<grid, 128 * HALVES + 128, T5_SMEM_BYTES, st>>>(a);
@@ -434,8 +438,9 @@ __global__ void sym5_finalize_kernel(const double* __restrict__ acc, long long n
     out[row * ldo + c] = (float)acc[row * T5_N + c];
 }
 
-int launch_sym_tc5(const float* zp, long long n, int CP, const float* nlc, const float* V16, int t, float* out, int ldo,
+int launch_sym_tc5(const float* zp, long long n, const Layout& lay, const float* nlc, const float* V16, int t, float* out, int ldo,
                    int rb_begin, int rb_end, void* workspace, size_t workspace_bytes, cudaStream_t st) {
+    const int CP = lay.CP, KP = lay.KP, G = lay.G;
     const int nblocks = (int)((n + T5_ROWS - 1) / T5_ROWS);
     const size_t acc_bytes = ((size_t)n * T5_N * sizeof(double) + 1023) & ~(size_t)1023;
     const size_t need = acc_bytes + (size_t)nblocks * 16384;
@@ -458,28 +463,36 @@ int launch_sym_tc5(const float* zp, long long n, int CP, const float* nlc, const
         a.half = nblocks / 2 + 1;
         a.rb_begin = rb_begin;
         static const int splits_env = [] { const char* e = getenv("RPGP_SYM_SPLITS"); return e ? atoi(e) : 0; }();
-        long long want = (148LL * 2 * 16 + nrb - 1) / nrb;
+        long long want = (148LL * 2 * 16 + (long long)nrb * lay.nchunks - 1) / ((long long)nrb * lay.nchunks);
         if (splits_env > 0) want = splits_env;
         want = std::max<long long>(1, std::min<long long>(want, a.half));
         a.nsplits = (int)want;
-        dim3 grid((unsigned)nrb, (unsigned)a.nsplits, 1);
-        // polynomial-exp2 pairs (kv_kernels.cuh::exp2_neg_poly2); RPGP_SYM_POLY_PAIRS overrides (tools sweep)
-        static const int np_env = [] { const char* e = getenv("RPGP_SYM_POLY_PAIRS"); return e ? atoi(e) : -1; }();
-        const int np = np_env >= 0 ? np_env : (CP >= 20 ? 2 : (CP >= 16 ? 1 : 0));
+        dim3 grid((unsigned)nrb, (unsigned)a.nsplits, (unsigned)lay.nchunks);
         int rc = ERR_UNSUPPORTED;
-        // two threads per row where the row's coordinates leave room in 96 registers; RPGP_SYM_HALVES overrides (tools sweep)
-        static const int halves_env = [] { const char* e = getenv("RPGP_SYM_HALVES"); return e ? atoi(e) : 0; }();
-        const int halves = halves_env ? halves_env : (CP <= 24 ? 2 : 1);
+        if (KP == 1) {
+            // polynomial-exp2 pairs (kv_kernels.cuh::exp2_neg_poly2); RPGP_SYM_POLY_PAIRS overrides (tools sweep)
+            static const int np_env = [] { const char* e = getenv("RPGP_SYM_POLY_PAIRS"); return e ? atoi(e) : -1; }();
+            const int np = np_env >= 0 ? np_env : (CP >= 20 ? 2 : (CP >= 16 ? 1 : 0));
+            // two threads per row where the row's coordinates leave room in 96 registers; RPGP_SYM_HALVES overrides (tools sweep)
+            static const int halves_env = [] { const char* e = getenv("RPGP_SYM_HALVES"); return e ? atoi(e) : 0; }();
+            const int halves = halves_env ? halves_env : (CP <= 24 ? 2 : 1);
 #define RPGP_SYM5_CASE(CPv, NPv)                                                                                       \
-        if (CP == CPv && np == NPv) {                                                                                  \
-            if constexpr (CPv <= 24) rc = halves == 2 ? run_sym5<CPv, NPv, 2>(a, grid, st) : run_sym5<CPv, NPv, 1>(a, grid, st); \
-            else rc = run_sym5<CPv, NPv, 1>(a, grid, st);                                                              \
-        }
-        RPGP_SYM5_CASE(4, 0) RPGP_SYM5_CASE(8, 0) RPGP_SYM5_CASE(12, 0) RPGP_SYM5_CASE(16, 0) RPGP_SYM5_CASE(16, 1)
-        RPGP_SYM5_CASE(20, 0) RPGP_SYM5_CASE(20, 1) RPGP_SYM5_CASE(20, 2) RPGP_SYM5_CASE(20, 3) RPGP_SYM5_CASE(24, 0) RPGP_SYM5_CASE(24, 2)
-        RPGP_SYM5_CASE(28, 0) RPGP_SYM5_CASE(28, 2) RPGP_SYM5_CASE(32, 0) RPGP_SYM5_CASE(32, 2)
+            if (CP == CPv && np == NPv) {                                                                              \
+                if constexpr (CPv <= 24) rc = halves == 2 ? run_sym5<CPv, 1, CPv, NPv, 2>(a, grid, st) : run_sym5<CPv, 1, CPv, NPv, 1>(a, grid, st); \
+                else rc = run_sym5<CPv, 1, CPv, NPv, 1>(a, grid, st);                                                  \
+            }
+            RPGP_SYM5_CASE(4, 0) RPGP_SYM5_CASE(8, 0) RPGP_SYM5_CASE(12, 0) RPGP_SYM5_CASE(16, 0) RPGP_SYM5_CASE(16, 1)
+            RPGP_SYM5_CASE(20, 0) RPGP_SYM5_CASE(20, 1) RPGP_SYM5_CASE(20, 2) RPGP_SYM5_CASE(20, 3) RPGP_SYM5_CASE(24, 0) RPGP_SYM5_CASE(24, 2)
+            RPGP_SYM5_CASE(28, 0) RPGP_SYM5_CASE(28, 2) RPGP_SYM5_CASE(32, 0) RPGP_SYM5_CASE(32, 2)
 #undef RPGP_SYM5_CASE
-        if (rc == ERR_UNSUPPORTED) set_error("mvm_sym: no kernel for CP=%d poly pairs=%d (compiled: 0 for every CP, 1 for CP 16/20, 2 for CP >= 20)", CP, np);
+            if (rc == ERR_UNSUPPORTED) set_error("mvm_sym: no kernel for CP=%d poly pairs=%d (compiled: 0 for every CP, 1 for CP 16/20, 2 for CP >= 20)", CP, np);
+        } else {
+            // K > 1: the (KP, G, CP) chunk shapes of dispatch.cuh; one MUFU per group, so no polynomial offload; two threads per row
+#define RPGP_SYM5_KN(KPv, Gv, CPv, TPv) if (KP == KPv && G == Gv && CP == CPv) rc = run_sym5<CPv, KPv, Gv, 0, 2>(a, grid, st);
+            RPGP_KN_SHAPE_LIST(RPGP_SYM5_KN, 0)
+#undef RPGP_SYM5_KN
+            if (rc == ERR_UNSUPPORTED) set_error("mvm_sym: no kernel for chunk shape KP=%d G=%d CP=%d", KP, G, CP);
+        }
         if (rc) return rc;
     }
     const long long total = n * t;

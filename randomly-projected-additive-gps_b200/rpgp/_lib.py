@@ -246,7 +246,7 @@ def mvm_sym(zp, lay, nlc, V, block_range=None, events=None):
     """Symmetric K(Z,Z) @ V on the tensor cores (every kernel value evaluated once).  block_range=(b0, b1) restricts to the
     unique block pairs owned by 128-row blocks [b0, b1): the result then holds partial sums for ALL rows (all-reduce it)."""
     require_cuda(zp, nlc, V)
-    assert zp.dtype == torch.float32 and zp.is_contiguous() and zp.shape[0] == 1
+    assert zp.dtype == torch.float32 and zp.is_contiguous() and zp.shape[0] == lay.nchunks
     lib = load()
     n, t = zp.shape[1], V.shape[1]
     assert V.shape[0] == n

@@ -25,7 +25,7 @@ SYM_ENABLED = os.environ.get("RPGP_SYM", "1") != "0"
 
 
 def _use_sym(p1, p2, t, row_range):
-    return (SYM_ENABLED and p2 is p1 and row_range is None and p1.n >= SYM_MIN_ROWS and p1.zp.shape[0] == 1
+    return (SYM_ENABLED and p2 is p1 and row_range is None and p1.n >= SYM_MIN_ROWS
             and _lib.mvm_sym_supported(p1.lay, min(t, 16)))
 
 

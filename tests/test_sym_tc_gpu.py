@@ -16,12 +16,12 @@ def rel(a, b):
     return np.linalg.norm(a - b) / max(np.linalg.norm(b), 1e-300)
 
 
-def setup(n, J, t, seed, spread=1.0):
+def setup(n, J, t, seed, spread=1.0, K=1):
     rng = np.random.RandomState(seed)
-    Z = (rng.randn(n, J) * spread).astype(np.float32)
+    Z = (rng.randn(n, J * K) * spread / np.sqrt(K)).astype(np.float32)
     c = (rng.rand(J) + 0.1).astype(np.float32)
     V = rng.randn(n, t).astype(np.float32)
-    lay = _lib.plan_layout(J, 1)
+    lay = _lib.plan_layout(J, K)
     zp = _lib.pack_coords(torch.from_numpy(Z).to(DEV), lay)
     nlc = _lib.pack_log2c(torch.from_numpy(c).to(DEV), lay)
     return Z, c, V, lay, zp, nlc
@@ -34,6 +34,18 @@ def test_sym_matches_oracle(n, J, t):
     assert _lib.mvm_sym_supported(lay, t)
     got = _lib.mvm_sym(zp, lay, nlc, torch.from_numpy(V).to(DEV)).cpu().numpy()
     ref = orc.kmv(Z, Z, c, J, 1, V)
+    assert np.isfinite(got).all()
+    assert rel(got, ref) < 1e-5, rel(got, ref)
+
+
+@pytest.mark.parametrize("n,J,K,t", [(300, 20, 5, 11), (1000, 1, 20, 11), (777, 3, 2, 4), (1025, 10, 3, 16), (640, 2, 16, 1),
+                                     (900, 40, 1, 11), (515, 90, 1, 3), (1300, 7, 8, 11), (260, 1, 32, 2)])
+def test_sym_group_and_chunked_layouts_match_oracle(n, J, K, t):
+    """K > 1 (one exponential per group of K coordinates) and J*K > 32 (several coordinate chunks, summed by the FP64 accumulators)."""
+    Z, c, V, lay, zp, nlc = setup(n, J, t, seed=n + J + K, K=K)
+    assert _lib.mvm_sym_supported(lay, t)
+    got = _lib.mvm_sym(zp, lay, nlc, torch.from_numpy(V).to(DEV)).cpu().numpy()
+    ref = orc.kmv(Z, Z, c, J, K, V)
     assert np.isfinite(got).all()
     assert rel(got, ref) < 1e-5, rel(got, ref)
 
@@ -59,6 +71,7 @@ def test_sym_block_ranges_sum_to_full():
 
 
 def test_sym_unsupported_shapes_are_reported():
-    assert not _lib.mvm_sym_supported(_lib.plan_layout(20, 5), 11)
-    assert not _lib.mvm_sym_supported(_lib.plan_layout(90, 1), 11)
+    assert _lib.mvm_sym_supported(_lib.plan_layout(20, 5), 11)
+    assert _lib.mvm_sym_supported(_lib.plan_layout(90, 1), 16)
     assert not _lib.mvm_sym_supported(_lib.plan_layout(20, 1), 17)
+    assert not _lib.mvm_sym_supported(_lib.plan_layout(20, 1), 0)
