@@ -16,8 +16,8 @@
 //
 // CTA = 128*HALVES arithmetic threads (setmaxnreg.inc) + 4 epilogue warps (setmaxnreg.dec).  HALVES = 1: thread = row, all 32
 // columns of a tile; HALVES = 2: two threads per row, 16 columns each -> 16 arithmetic warps per SM at <= 96 registers, which
-// hides the MUFU / FADD2 latencies that two warps per scheduler cannot.  Lane 0 of the first epilogue warp also issues the MMAs
-// of a tile, lane 0 of the second one the bulk copies (all buffers are released by the tile's tcgen05.commit).
+// hides the MUFU / FADD2 latencies that two warps per scheduler cannot.  Lane 0 of epilogue warps 0 and 2 also issue the row-side and
+// the column-side MMAs of a tile, lane 0 of epilogue warp 1 the bulk copies (all buffers are released by the two tcgen05.commit of a tile).
 #include <algorithm>
 #include <cstdlib>
 
@@ -62,7 +62,7 @@ constexpr uint32_t T5_SMEM_BYTES = T5_BAR + 256 + 1024;
 constexpr int B5_ZFULL = 0;      // [3]  bulk copy -> arithmetic warps
 constexpr int B5_BFULL = 3;      // [2]  bulk copy -> MMA issuer (row-side B tile)
 constexpr int B5_SFULL = 5;      // [2]  arithmetic warps -> MMA issuer (count 4)
-constexpr int B5_TDONE = 7;      // [2]  tcgen05.commit of a tile: S / B / z stages reusable, D2 readable, D1 of a closed epoch readable
+constexpr int B5_TDONE = 7;      // [2]  tcgen05.commit of both issuers (count 2): S / B / z stages reusable, D2 readable, closed D1 epochs readable
 constexpr int B5_EREAD = 9;      // [2]  epilogue warps have read D2 (count 4)
 constexpr int B5_D1EMPTY = 11;   // [2]  arithmetic warps have folded an epoch of D1 (count 4)
 constexpr int B5_BCFULL = 13;    // [1]  bulk copy of the column-side B operand
@@ -188,7 +188,7 @@ __global__ void __launch_bounds__(128 * HALVES + 128, 2) mvm_sym_tc5_kernel(cons
         for (int b = 0; b < 2; ++b) {
             mbar_init(&bars[B5_BFULL + b], 1);
             mbar_init(&bars[B5_SFULL + b], AW);
-            mbar_init(&bars[B5_TDONE + b], 1);
+            mbar_init(&bars[B5_TDONE + b], 2);
             mbar_init(&bars[B5_EREAD + b], 4);
             mbar_init(&bars[B5_D1EMPTY + b], AW);
         }
@@ -293,7 +293,8 @@ __global__ void __launch_bounds__(128 * HALVES + 128, 2) mvm_sym_tc5_kernel(cons
         // =========================================== epilogue warps (+ MMA issue, + bulk copies) ========================
         asm volatile("setmaxnreg.dec.sync.aligned.u32 %0;" ::"n"(REGS_HELP));
         const int qd = warp - AW;                                  // TMEM lane quadrant (AW is a multiple of 4)
-        const bool issuer = (qd == 0 && lane == 0), loader = (qd == 1 && lane == 0);
+        // two issuing threads (a UTCHMMA blocks its warp ~100 clk whatever its size): row side from quadrant 0, column side from quadrant 2
+        const bool row_issuer = (qd == 0 && lane == 0), col_issuer = (qd == 2 && lane == 0), loader = (qd == 1 && lane == 0);
         constexpr uint32_t IDESC_ROW_N32 = idesc5_tf32(128, 2 * T5_N, 0, 0), IDESC_ROW_N16 = idesc5_tf32(128, T5_N, 0, 0);
         constexpr uint32_t IDESC_COL = idesc5_tf32(64, 2 * T5_N, 1, 0);
         const unsigned char* bsplit = reinterpret_cast<const unsigned char*>(a.bsplit);
@@ -328,16 +329,14 @@ __global__ void __launch_bounds__(128 * HALVES + 128, 2) mvm_sym_tc5_kernel(cons
         for (int t = it.next_live(0); t < it.ntiles; t = it.next_live(t + 1), ++j) {
             const int b = j & 1;
             const bool diag = it.diag(t);
-            if (issuer) {
+            if (row_issuer) {   // D1 += Sh.[Vh|Vl] + Sl.Vh, four k-steps of 8 tile columns
                 const int e = j / T5_F;
                 mbar5_wait_sleep(&bars[B5_BFULL + b], (uint32_t)((j >> 1) & 1));
-                if (j == 0) mbar5_wait_sleep(&bars[B5_BCFULL], 0u);
-                if (j >= 2) mbar5_wait_sleep(&bars[B5_EREAD + b], (uint32_t)(((j >> 1) - 1) & 1));        // D2[b] has been read
                 if (j % T5_F == 0 && e >= 2) mbar5_wait_sleep(&bars[B5_D1EMPTY + (e & 1)], (uint32_t)(((e >> 1) - 1) & 1));
                 mbar5_wait_sleep(&bars[B5_SFULL + b], (uint32_t)((j >> 1) & 1));
                 tc5_fence_after();
-                const uint32_t sbuf = base + T5_S + (uint32_t)b * 32768u;
-                if (!(T5_DIAG & 4)) {   // row side: D1 += Sh.[Vh|Vl] + Sl.Vh, four k-steps of 8 tile columns
+                if (!(T5_DIAG & 4)) {
+                    const uint32_t sbuf = base + T5_S + (uint32_t)b * 32768u;
                     const uint32_t d1 = tmem + 32u * (uint32_t)(e & 1);
                     const uint64_t dA_h = smem_desc5(sbuf, 512, 512, LAYOUT5_SW128_BASE32B);
                     const uint64_t dA_l = smem_desc5(sbuf + 16384u, 512, 512, LAYOUT5_SW128_BASE32B);
@@ -348,9 +347,16 @@ __global__ void __launch_bounds__(128 * HALVES + 128, 2) mvm_sym_tc5_kernel(cons
                         umma5(d1, dA_l + (uint64_t)(ks * 2), dB + (uint64_t)(ks * 2), IDESC_ROW_N16, 1u);
                     }
                 }
-                if (!diag && !(T5_DIAG & 2)) {   // column side: D2 = [Sh ; Sl]^T . [Vh|Vl], sixteen k-steps of 8 tile rows
+                umma5_commit(&bars[B5_TDONE + b]);
+            }
+            if (col_issuer) {   // D2 = [Sh ; Sl]^T . [Vh|Vl], sixteen k-steps of 8 tile rows (nothing to do on the diagonal block)
+                if (j == 0) mbar5_wait_sleep(&bars[B5_BCFULL], 0u);
+                if (j >= 2) mbar5_wait_sleep(&bars[B5_EREAD + b], (uint32_t)(((j >> 1) - 1) & 1));        // D2[b] has been read
+                mbar5_wait_sleep(&bars[B5_SFULL + b], (uint32_t)((j >> 1) & 1));
+                tc5_fence_after();
+                if (!diag && !(T5_DIAG & 2)) {
                     const uint32_t d2 = tmem + 64u + 32u * (uint32_t)b;
-                    const uint64_t dA = smem_desc5(sbuf, 16384, 512, LAYOUT5_SW128_BASE32B);
+                    const uint64_t dA = smem_desc5(base + T5_S + (uint32_t)b * 32768u, 16384, 512, LAYOUT5_SW128_BASE32B);
                     const uint64_t dB = smem_desc5(base + T5_BC, 16, 1024, LAYOUT5_SW128);
 #pragma unroll
                     for (int g = 0; g < 16; ++g)
