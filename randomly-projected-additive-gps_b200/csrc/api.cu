@@ -212,11 +212,6 @@ int rpgp_mvm_sym_f32(const float* zp, int64_t n, const rpgp_layout* lay, const f
     const int nblocks = (int)((n + 127) / 128);
     RPGP_REQUIRE(0 <= row_block_begin && row_block_begin <= row_block_end && row_block_end <= nblocks,
                  "mvm_sym: row block range [%d, %d) outside [0, %d]", row_block_begin, row_block_end, nblocks);
-    // RPGP_SYM_KERNEL=3 selects the earlier variant (row side in registers) for A/B runs
-    static const int variant = [] { const char* e = getenv("RPGP_SYM_KERNEL"); return e ? atoi(e) : 5; }();
-    if (variant == 3 && lay->K == 1 && lay->nchunks == 1)
-        return launch_sym_tc3(zp, n, lay->CP, neg_log2c, Vp16, t, out, ldo, row_block_begin, row_block_end, workspace,
-                              workspace_bytes, (cudaStream_t)stream);
     return launch_sym_tc5(zp, n, *reinterpret_cast<const Layout*>(lay), neg_log2c, Vp16, t, out, ldo, row_block_begin, row_block_end, workspace,
                           workspace_bytes, (cudaStream_t)stream);
 }

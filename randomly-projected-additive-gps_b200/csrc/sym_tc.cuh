@@ -1,4 +1,4 @@
-// sym_tc.cuh -- launcher of the symmetric tensor-core K(Z,Z).V kernel (sym_tc3.cu; earlier variants live in experiments/)
+// sym_tc.cuh -- launcher of the symmetric tensor-core K(Z,Z).V kernel (sym_tc5.cu; earlier variants live in experiments/)
 #pragma once
 #include "rpgp_common.cuh"
 
@@ -10,8 +10,5 @@ inline size_t sym_workspace_bytes(long long n) {
 // both uses of every kernel value on the tensor cores (sym_tc5.cu): the default
 struct Layout;
 int launch_sym_tc5(const float* zp, long long n, const Layout& lay, const float* nlc, const float* V16, int t, float* out, int ldo,
-                   int rb_begin, int rb_end, void* workspace, size_t workspace_bytes, cudaStream_t st);
-// warp-specialised variant (sym_tc3.cu): row side in registers, column side on the tensor cores issued by dedicated warps
-int launch_sym_tc3(const float* zp, long long n, int CP, const float* nlc, const float* V16, int t, float* out, int ldo,
                    int rb_begin, int rb_end, void* workspace, size_t workspace_bytes, cudaStream_t st);
 }  // namespace rpgp
