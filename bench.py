@@ -325,6 +325,20 @@ def run_ours(args, w):
     else:
         np2 = int(os.environ.get("RPGP_POLY_PAIRS", 0 if TPb > 16 else (3 if lay.CP >= 28 else 2 if lay.CP >= 16 else 1 if lay.CP >= 8 else 0)))
     evals = (float(n) * n / 2 / world) if use_sym else float(m_rows) * n          # kernel values actually formed by this rank
+    # K > 1 symmetric products: squared distances on tcgen05 (csrc/sym_tcd.cu) while the centred coordinates stay inside the gate
+    tcd = _lib.mvm_sym_distance_plan(lay) if (use_sym and K > 1) else None
+    if tcd is not None:
+        zc = zp - zp.mean(dim=1, keepdim=True)                 # packed planes are already scaled by sqrt(log2(e)/2)
+        max_norm2 = max(float((zc[ch, :, g * lay.KP:g * lay.KP + K] ** 2).sum(-1).max())
+                        for ch in range(lay.nchunks) for g in range(lay.G) if ch * lay.G + g < J)
+        del zc
+        tcd["max_centred_norm2"] = max_norm2
+        if max_norm2 > tcd["bound"]:
+            tcd = dict(tcd, active=False)
+        else:
+            tcd = dict(tcd, active=True)
+            groups = tcd["nchunks"] * tcd["groups_per_chunk"]
+            fp32_alg = float(m_rows) * n * (2 * J + t)       # FP32 lane-ops with the distance on the tensor cores
     xu_ex2 = evals * (groups - 2 * np2)
     hbm_peak = None
     try:
@@ -341,8 +355,11 @@ def run_ours(args, w):
         "bound": "mufu", "achieved": ach / 1e12, "peak": mufu_peak / 1e12, "unit": "Tex2/s", "frac": ach / mufu_peak,
         "peak_source": "measured live: rpgp_measure_peaks mufu_ex2 %.2f/clk/SM x %d SMs x %.0f MHz"
                        % (peaks["mufu_ex2"]["mufu_per_clk_sm"], sms, peaks["mufu_ex2"]["mhz"]),
-        "kernel": ("mvm_sym_tc5_kernel<CP=%d,NP2=%d> (symmetric: each kernel value evaluated once; S.V and S^T.V both on tcgen05 "
-                   "kind::tf32, 3xTF32 split)" % (lay.CP, np2)) if use_sym
+        "kernel": ("mvm_sym_tcd_kernel<NL=%d> (symmetric; squared distances as augmented inner products on tcgen05 kind::tf32, "
+                   "3xTF32, %d groups x %d k-steps per chunk; S.V and S^T.V on tcgen05 as well)"
+                   % (tcd["lines"], tcd["groups_per_chunk"], tcd["ksteps_per_group"])) if (tcd is not None and tcd["active"])
+                  else ("mvm_sym_tc5_kernel<CP=%d,NP2=%d> (symmetric: each kernel value evaluated once; S.V and S^T.V both on tcgen05 "
+                        "kind::tf32, 3xTF32 split)" % (lay.CP, np2)) if use_sym
                   else "mvm_fwd_kernel<CP=%d,TP=%d,KP=%d,G=%d,NP2=%d>" % (lay.CP, TPb, lay.KP, lay.G, np2),
         "note": "achieved counts the ALGORITHMIC exponentials of SURVEY 8(d) (m*n*J per product), so frac can exceed 1: "
                 + ("symmetry halves the evaluations and " if use_sym else "")
@@ -351,7 +368,7 @@ def run_ours(args, w):
         "kernel_ms": kernel_ms, "kernel_share_of_step": kernel_ms / ms_per_step,
         "algorithmic_ex2_per_launch": ex2_alg, "xu_ex2_per_launch": xu_ex2, "xu_frac": xu_ex2 / (kernel_ms * 1e-3) / mufu_peak,
         "fp32_frac": (fp32_alg / (kernel_ms * 1e-3)) / fp32_peak, "fp32_peak_Tlaneops": fp32_peak / 1e12,
-        "traffic": traffic,
+        "traffic": traffic, "distance_on_tensor_cores": tcd,
         "hbm": {"algorithmic_bytes_per_launch": alg_bytes, "achieved_GBps": alg_bytes / (kernel_ms * 1e-3) / 1e9,
                 "peak_GBps": hbm_peak, "frac": (alg_bytes / (kernel_ms * 1e-3) / 1e9 / hbm_peak) if hbm_peak else None,
                 "peak_source": "MEASURED_PEAKS.json" if hbm_peak else "absent"},

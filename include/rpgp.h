@@ -97,6 +97,13 @@ int rpgp_mvm_fwd_f32(const float* z1p, int64_t m, int64_t z1_stride, const float
  * sub-range (one rank of a multi-GPU job) the outputs of the ranks must be summed (all-reduce).
  * Accumulation uses FP64 atomics, so results are reproducible to FP32 rounding but not bit-identical run to run. */
 size_t rpgp_mvm_sym_workspace_bytes(int64_t n, const rpgp_layout* lay);
+/* K > 1 (4 <= K <= 24): the squared distances |z|^2 + |z'|^2 - 2 z.z' are evaluated on tcgen05 as augmented inner products
+ * (3xTF32, centred coordinates) while the largest centred, scaled squared group norm max_i,g |z_ig - mean_g|^2 stays within
+ * rpgp_mvm_sym_distance_bound(); a device-side flag written by the operand pre-pass decides per call, beyond the bound the
+ * direct-difference kernel runs (no host synchronisation either way).  rpgp_mvm_sym_distance_plan reports the chunking of that path:
+ * plan = {supported, groups per chunk, k-steps of 8 per group, 128-byte operand lines per row, chunks}. */
+float rpgp_mvm_sym_distance_bound(void);
+int rpgp_mvm_sym_distance_plan(const rpgp_layout* lay, int plan[5]);
 int rpgp_mvm_sym_supported(const rpgp_layout* lay, int t);
 int rpgp_mvm_sym_f32(const float* zp, int64_t n, const rpgp_layout* lay, const float* neg_log2c, const float* Vp16, int t,
                      float* out, int ldo, int row_block_begin, int row_block_end, void* workspace, size_t workspace_bytes,

@@ -194,7 +194,17 @@ int rpgp_mvm_fwd_f32(const float* z1p, int64_t m, int64_t z1_stride, const float
 
 size_t rpgp_mvm_sym_workspace_bytes(int64_t n, const rpgp_layout* lay) {
     if (!lay || n <= 0) return 0;
-    return sym_workspace_bytes(n);
+    return sym_workspace_bytes(n, *reinterpret_cast<const Layout*>(lay));
+}
+
+float rpgp_mvm_sym_distance_bound(void) { return tcd_gate_bound(); }
+
+int rpgp_mvm_sym_distance_plan(const rpgp_layout* lay, int plan[5]) {
+    if (int rc = check_layout(lay)) return rc;
+    RPGP_REQUIRE(plan != nullptr, "mvm_sym_distance_plan: NULL pointer");
+    const TcdPlan p = plan_tcd(*reinterpret_cast<const Layout*>(lay));
+    plan[0] = p.supported; plan[1] = p.GT; plan[2] = p.KS; plan[3] = p.NL; plan[4] = p.nchunks;
+    return OK;
 }
 
 int rpgp_mvm_sym_supported(const rpgp_layout* lay, int t) {

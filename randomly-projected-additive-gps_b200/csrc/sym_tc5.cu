@@ -20,19 +20,20 @@
 // the column-side MMAs of a tile, lane 0 of epilogue warp 1 the bulk copies (all buffers are released by the two tcgen05.commit of a tile).
 #include <algorithm>
 #include <cstdlib>
+#include <cstring>
 
 #include "aux_kernels.cuh"
 #include "dispatch.cuh"
 #include "kv_kernels.cuh"
 #include "sym_tc.cuh"
+#include "sym_tc_dev.cuh"
 
 namespace rpgp {
 
 namespace {
 
-constexpr int T5_ROWS = 128;     // rows per CTA
-constexpr int T5_BN = 32;        // columns per tile
-constexpr int T5_N = 16;         // padded right-hand sides
+using namespace tcdev;
+
 constexpr int T5_F = 4;          // tiles accumulated in TMEM per row-side epoch (K = 128 per flush, like the column side)
 constexpr int T5_ZST = 3;        // coordinate-tile stages
 #ifndef T5_QUNROLL
@@ -67,94 +68,18 @@ constexpr int B5_EREAD = 9;      // [2]  epilogue warps have read D2 (count 4)
 constexpr int B5_D1EMPTY = 11;   // [2]  arithmetic warps have folded an epoch of D1 (count 4)
 constexpr int B5_BCFULL = 13;    // [1]  bulk copy of the column-side B operand
 
-constexpr uint32_t LAYOUT5_SW128 = 2, LAYOUT5_SW128_BASE32B = 1;
-__device__ __forceinline__ uint64_t smem_desc5(uint32_t saddr, uint32_t lbo_bytes, uint32_t sbo_bytes, uint32_t layout) {
-    return (uint64_t)((saddr >> 4) & 0x3FFF) | ((uint64_t)((lbo_bytes >> 4) & 0x3FFF) << 16) |
-           ((uint64_t)((sbo_bytes >> 4) & 0x3FFF) << 32) | (1ull << 46) | ((uint64_t)layout << 61);
-}
-__host__ __device__ constexpr uint32_t idesc5_tf32(int M, int N, int a_mn_major, int b_mn_major) {
-    return (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)a_mn_major << 15) | ((uint32_t)b_mn_major << 16) |
-           ((uint32_t)(N >> 3) << 17) | ((uint32_t)(M >> 4) << 24);
-}
-__device__ __forceinline__ void umma5(uint32_t d_tmem, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t accumulate) {
-    asm volatile(
-        "{\n\t"
-        ".reg .pred p;\n\t"
-        "setp.ne.b32 p, %4, 0;\n\t"
-        "tcgen05.mma.cta_group::1.kind::tf32 [%0], %1, %2, %3, p;\n\t"
-        "}\n" ::"r"(d_tmem), "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate)
-        : "memory");
-}
-__device__ __forceinline__ void umma5_commit(uint64_t* bar) {
-    asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(bar)) : "memory");
-}
-__device__ __forceinline__ void mbar5_arrive(uint64_t* bar) {
-    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
-}
-// helper warps poll with a back-off so that their spinning does not take issue slots from the arithmetic warps
-__device__ __forceinline__ void mbar5_wait_sleep(uint64_t* bar, uint32_t parity) {
-    uint32_t done = 0;
-    while (true) {
-        asm volatile(
-            "{\n\t.reg .pred p;\n\t"
-            "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
-            "selp.u32 %0, 1, 0, p;\n\t}\n"
-            : "=r"(done)
-            : "r"(smem_u32(bar)), "r"(parity)
-            : "memory");
-        if (done) break;
-        __nanosleep(64);
-    }
-}
-__device__ __forceinline__ void tc5_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
-__device__ __forceinline__ void tc5_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
-__device__ __forceinline__ void fence5_async_smem() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
-__device__ __forceinline__ void tmem5_ld16(uint32_t taddr, float* v) {
-    uint32_t r[16];
-    asm volatile(
-        "tcgen05.ld.sync.aligned.32x32b.x16.b32 {%0,%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15}, [%16];"
-        : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]),
-          "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15])
-        : "r"(taddr));
-    asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
-#pragma unroll
-    for (int q = 0; q < 16; ++q) v[q] = __uint_as_float(r[q]);
-}
-__device__ __forceinline__ void tmem5_ld8(uint32_t taddr, float* v) {
-    uint32_t r[8];
-    asm volatile("tcgen05.ld.sync.aligned.32x32b.x8.b32 {%0,%1,%2,%3,%4,%5,%6,%7}, [%8];"
-                 : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7])
-                 : "r"(taddr));
-    asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
-#pragma unroll
-    for (int q = 0; q < 8; ++q) v[q] = __uint_as_float(r[q]);
-}
-__device__ __forceinline__ float tf32_hi5(float x) { return __uint_as_float(__float_as_uint(x) & 0xFFFFE000u); }
-__host__ __device__ __forceinline__ uint32_t sw128_5(uint32_t row, uint32_t kk) {
-    return row * 128u + ((((kk >> 2) ^ (row & 7u)) << 4) | ((kk & 3u) << 2));
-}
 
 struct Sym5Args {
     const float* z;        // [nchunks][n][CP]  (blockIdx.z = coordinate chunk; the chunks' kernel values add up, so do their products)
     const float* bsplit;   // [nblocks*4][4096 B] pre-split right-hand sides (B operands)
     const float* nlc;      // [nchunks][CP or G]
     double* acc;           // [n][16] FP64 accumulators (zeroed by the launcher)
+    const unsigned* gate;  // K > 1 only: bits of max |z_group|^2 written by sym_tcd.cu's pre-pass (NULL: always run)
+    unsigned gate_min;     // run only when *gate > gate_min (below, the distance-on-tensor-core kernel has taken the launch)
     long long n;
     int nblocks, half, nsplits, rb_begin;
 };
 
-
-// tile enumeration shared by all roles: offsets k in [k_begin, k_end), four 32-column tiles per 128-column block
-struct Tile5Iter {
-    int I, B, k_begin, ntiles;
-    long long n;
-    __device__ __forceinline__ int block_of(int k) const { int Ip = I + k; return Ip >= B ? Ip - B : Ip; }
-    __device__ __forceinline__ bool offset_active(int k) const { return !((B % 2 == 0) && (k == B / 2) && (I >= B / 2)); }
-    __device__ __forceinline__ long long col0(int t) const { return (long long)block_of(k_begin + (t >> 2)) * T5_ROWS + (t & 3) * T5_BN; }
-    __device__ __forceinline__ bool live(int t) const { return offset_active(k_begin + (t >> 2)) && col0(t) < n; }
-    __device__ __forceinline__ bool diag(int t) const { return block_of(k_begin + (t >> 2)) == I; }
-    __device__ __forceinline__ int next_live(int t) const { while (t < ntiles && !live(t)) ++t; return t; }
-};
 
 }  // namespace
 
@@ -164,6 +89,7 @@ __global__ void __launch_bounds__(128 * HALVES + 128, 2) mvm_sym_tc5_kernel(cons
     constexpr int AW = 4 * HALVES;                 // arithmetic warps
     constexpr int FC = T5_N / HALVES;              // right-hand-side columns folded by one arithmetic warp
     constexpr int REGS_ARITH = HALVES == 1 ? T5_REGS_ARITH : 96, REGS_HELP = HALVES == 1 ? T5_REGS_HELP : 48;
+    if (KP > 1 && a.gate != nullptr && *a.gate <= a.gate_min) return;
     extern __shared__ unsigned char smem_raw[];
     const uint32_t base = (smem_u32(smem_raw) + 1023u) & ~1023u;
     unsigned char* sm = smem_raw + (base - smem_u32(smem_raw));
@@ -449,6 +375,7 @@ int launch_sym_tc5(const float* zp, long long n, const Layout& lay, const float*
     const int CP = lay.CP, KP = lay.KP, G = lay.G;
     const int nblocks = (int)((n + T5_ROWS - 1) / T5_ROWS);
     const size_t acc_bytes = ((size_t)n * T5_N * sizeof(double) + 1023) & ~(size_t)1023;
+    const size_t base_bytes = sym_base_workspace_bytes(n);
     const size_t need = acc_bytes + (size_t)nblocks * 16384;
     if (workspace == nullptr || workspace_bytes < need) {
         set_error("mvm_sym: workspace %zu bytes < required %zu", workspace_bytes, need);
@@ -465,6 +392,7 @@ int launch_sym_tc5(const float* zp, long long n, const Layout& lay, const float*
         RPGP_CUDA_OK(cudaGetLastError());
         Sym5Args a;
         a.z = zp; a.bsplit = bsplit; a.nlc = nlc; a.acc = acc; a.n = n;
+        a.gate = nullptr; a.gate_min = 0;
         a.nblocks = nblocks;
         a.half = nblocks / 2 + 1;
         a.rb_begin = rb_begin;
@@ -493,6 +421,17 @@ int launch_sym_tc5(const float* zp, long long n, const Layout& lay, const float*
 #undef RPGP_SYM5_CASE
             if (rc == ERR_UNSUPPORTED) set_error("mvm_sym: no kernel for CP=%d poly pairs=%d (compiled: 0 for every CP, 1 for CP 16/20, 2 for CP >= 20)", CP, np);
         } else {
+            // K > 1, squared distances on the tensor cores (sym_tcd.cu) while the coordinates are small enough for the cancellation
+            // in |z|^2 + |z'|^2 - 2 z.z'; the direct-difference kernel below then returns at once (and the other way round)
+            if (plan_tcd(lay).supported && workspace_bytes >= base_bytes + tcd_workspace_bytes(n, lay)) {
+                const unsigned* gate = nullptr;
+                if (int rcd = launch_sym_tcd(zp, n, lay, nlc, bsplit, acc, nblocks, rb_begin, nrb, (unsigned char*)workspace + base_bytes,
+                                             workspace_bytes - base_bytes, &gate, st))
+                    return rcd;
+                a.gate = gate;
+                const float bound = tcd_gate_bound();
+                memcpy(&a.gate_min, &bound, sizeof(float));
+            }
             // K > 1: the (KP, G, CP) chunk shapes of dispatch.cuh; one MUFU per group, so no polynomial offload; two threads per row
 #define RPGP_SYM5_KN(KPv, Gv, CPv, TPv) if (KP == KPv && G == Gv && CP == CPv) rc = run_sym5<CPv, KPv, Gv, 0, 2>(a, grid, st);
             RPGP_KN_SHAPE_LIST(RPGP_SYM5_KN, 0)

@@ -45,6 +45,8 @@ SIGNATURES = {
                                  c_void_p, c_int, c_void_p, c_int, c_void_p, c_size_t, c_void_p]),
     "rpgp_mvm_sym_workspace_bytes": (c_size_t, [c_int64, POINTER(Layout)]),
     "rpgp_mvm_sym_supported": (c_int, [POINTER(Layout), c_int]),
+    "rpgp_mvm_sym_distance_bound": (ctypes.c_float, []),
+    "rpgp_mvm_sym_distance_plan": (c_int, [POINTER(Layout), POINTER(c_int)]),
     "rpgp_mvm_sym_f32": (c_int, [c_void_p, c_int64, POINTER(Layout), c_void_p, c_void_p, c_int, c_void_p, c_int, c_int,
                                  c_int, c_void_p, c_size_t, c_void_p]),
     "rpgp_quad_workspace_bytes": (c_size_t, [c_int64, c_int64, POINTER(Layout), c_int]),
@@ -240,6 +242,16 @@ def mvm_fwd(z1p, z2p, lay, nlc, V, row_range=None, events=None):
 
 def mvm_sym_supported(lay, t):
     return bool(load().rpgp_mvm_sym_supported(ctypes.byref(lay), int(t)))
+
+
+def mvm_sym_distance_plan(lay):
+    """chunking of the distance-on-tensor-core path for K > 1 (csrc/sym_tcd.cu), or None when the layout does not use it"""
+    plan = (c_int * 5)()
+    _check(load().rpgp_mvm_sym_distance_plan(ctypes.byref(lay), plan), "rpgp_mvm_sym_distance_plan")
+    if not plan[0]:
+        return None
+    return dict(groups_per_chunk=plan[1], ksteps_per_group=plan[2], lines=plan[3], nchunks=plan[4],
+                bound=float(load().rpgp_mvm_sym_distance_bound()))
 
 
 def mvm_sym(zp, lay, nlc, V, block_range=None, events=None):

@@ -75,3 +75,64 @@ def test_sym_unsupported_shapes_are_reported():
     assert _lib.mvm_sym_supported(_lib.plan_layout(90, 1), 16)
     assert not _lib.mvm_sym_supported(_lib.plan_layout(20, 1), 17)
     assert not _lib.mvm_sym_supported(_lib.plan_layout(20, 1), 0)
+
+
+# ---- K > 1 with the squared distances on the tensor cores (csrc/sym_tcd.cu) ------------------------------------------------------
+@pytest.mark.parametrize("n,J,K,t", [(300, 20, 5, 11), (1000, 1, 20, 11), (1025, 10, 4, 16), (640, 2, 16, 1), (1300, 7, 8, 11),
+                                     (260, 1, 24, 2), (3000, 3, 6, 5), (129, 9, 5, 3), (4000, 20, 5, 11), (2000, 17, 7, 4)])
+def test_tensor_core_distances_match_oracle(n, J, K, t):
+    """4 <= K <= 24: U = |z|^2 + |z'|^2 - 2 z.z' as one augmented inner product on tcgen05 (3xTF32), several groups per chunk,
+    several chunks, partial last blocks; same 1e-5 bound as every other forward path."""
+    Z, c, V, lay, zp, nlc = setup(n, J, t, seed=7 * n + J + K, K=K)
+    got = _lib.mvm_sym(zp, lay, nlc, torch.from_numpy(V).to(DEV)).cpu().numpy()
+    ref = orc.kmv(Z, Z, c, J, K, V)
+    assert np.isfinite(got).all()
+    assert rel(got, ref) < 1e-5, rel(got, ref)
+
+
+def _two_clusters(n, J, K, R2, seed, offset=0.0):
+    """every within-cluster pair is near (k ~ 1) while the scaled |z|^2 ~ R2 is large: the worst case for the cancellation"""
+    rng = np.random.RandomState(seed)
+    R = np.sqrt(R2 / 0.72134752 / K)
+    sign = np.where(rng.rand(n, 1) < 0.5, -1.0, 1.0)
+    Z = (sign * R + 0.3 * rng.randn(n, J * K) / np.sqrt(K) + offset).astype(np.float32)
+    c = (rng.rand(J) + 0.1).astype(np.float32)
+    lay = _lib.plan_layout(J, K)
+    zp = _lib.pack_coords(torch.from_numpy(Z).to(DEV), lay)
+    nlc = _lib.pack_log2c(torch.from_numpy(c).to(DEV), lay)
+    return Z, c, lay, zp, nlc
+
+
+@pytest.mark.parametrize("J,K,R2,offset", [(20, 5, 128.0, 0.0), (1, 20, 128.0, 0.0), (8, 6, 64.0, 0.0), (20, 5, 32.0, 25.0)])
+def test_tensor_core_distances_worst_case_radius(J, K, R2, offset):
+    """tight clusters far from the origin (below the gate, so the tensor-core path runs), with and without a common offset
+    (removed by the centring of the operand images); the systematic part of the error is what K.1 shows"""
+    n, t = 3000, 11
+    Z, c, lay, zp, nlc = _two_clusters(n, J, K, R2, seed=int(R2) + J, offset=offset)
+    V = np.random.RandomState(5).randn(n, t).astype(np.float32)
+    V[:, 0] = 1.0
+    got = _lib.mvm_sym(zp, lay, nlc, torch.from_numpy(V).to(DEV)).cpu().numpy()
+    ref = orc.kmv(Z, Z, c, J, K, V)
+    assert rel(got, ref) < 1e-5, rel(got, ref)
+    assert rel(got[:, 0], ref[:, 0]) < 1e-5, rel(got[:, 0], ref[:, 0])
+
+
+def test_tensor_core_distances_gate_hands_over_to_direct_differences():
+    """beyond the radius bound the pre-pass flag sends the launch to the direct-difference kernel: the result keeps that kernel's
+    accuracy (the tensor-core distances would be ~4e-5 off here, tools/tcd_check.py adv)"""
+    n, t, J, K = 3000, 11, 20, 5
+    Z, c, lay, zp, nlc = _two_clusters(n, J, K, 2048.0, seed=11)
+    V = np.random.RandomState(6).randn(n, t).astype(np.float32)
+    got = _lib.mvm_sym(zp, lay, nlc, torch.from_numpy(V).to(DEV)).cpu().numpy()
+    assert rel(got, orc.kmv(Z, Z, c, J, K, V)) < 3e-6
+
+
+def test_tensor_core_distances_block_ranges_sum_to_full():
+    Z, c, V, lay, zp, nlc = setup(1500, 20, 11, seed=3, K=5)
+    Vd = torch.from_numpy(V).to(DEV)
+    full = _lib.mvm_sym(zp, lay, nlc, Vd).cpu().numpy().astype(np.float64)
+    nb = (1500 + 127) // 128
+    parts = sum(_lib.mvm_sym(zp, lay, nlc, Vd, block_range=(b0, b1)).cpu().numpy().astype(np.float64)
+                for b0, b1 in [(0, 4), (4, 9), (9, nb)])
+    assert rel(parts, full) < 2e-6
+    assert rel(full, orc.kmv(Z, Z, c, 20, 5, V)) < 1e-5
