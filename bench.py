@@ -329,11 +329,12 @@ def run_ours(args, w):
     tcd = _lib.mvm_sym_distance_plan(lay) if (use_sym and K > 1) else None
     if tcd is not None:
         zc = zp - zp.mean(dim=1, keepdim=True)                 # packed planes are already scaled by sqrt(log2(e)/2)
-        max_norm2 = max(float((zc[ch, :, g * lay.KP:g * lay.KP + K] ** 2).sum(-1).max())
-                        for ch in range(lay.nchunks) for g in range(lay.G) if ch * lay.G + g < J)
-        del zc
-        tcd["max_centred_norm2"] = max_norm2
-        if max_norm2 > tcd["bound"]:
+        r2 = torch.stack([(zc[ch, :, g * lay.KP:g * lay.KP + K] ** 2).sum(-1)
+                          for ch in range(lay.nchunks) for g in range(lay.G) if ch * lay.G + g < J])
+        max_norm2, rms_norm2 = float(r2.max()), float((r2.double() ** 2).mean().sqrt())
+        del zc, r2
+        tcd["max_centred_norm2"], tcd["rms_centred_norm2"] = max_norm2, rms_norm2
+        if rms_norm2 > tcd["bound"] or max_norm2 > 10 * tcd["bound"]:      # the device-side gate of csrc/sym_tcd.cu (tcd_gate)
             tcd = dict(tcd, active=False)
         else:
             tcd = dict(tcd, active=True)

@@ -98,9 +98,9 @@ int rpgp_mvm_fwd_f32(const float* z1p, int64_t m, int64_t z1_stride, const float
  * Accumulation uses FP64 atomics, so results are reproducible to FP32 rounding but not bit-identical run to run. */
 size_t rpgp_mvm_sym_workspace_bytes(int64_t n, const rpgp_layout* lay);
 /* K > 1 (4 <= K <= 24): the squared distances |z|^2 + |z'|^2 - 2 z.z' are evaluated on tcgen05 as augmented inner products
- * (3xTF32, centred coordinates) while the largest centred, scaled squared group norm max_i,g |z_ig - mean_g|^2 stays within
- * rpgp_mvm_sym_distance_bound(); a device-side flag written by the operand pre-pass decides per call, beyond the bound the
- * direct-difference kernel runs (no host synchronisation either way).  rpgp_mvm_sym_distance_plan reports the chunking of that path:
+ * (3xTF32, centred coordinates) while the centred, scaled squared group norms r2 = |z_ig - mean_g|^2 stay small enough for the
+ * cancellation: sqrt(mean r2^2) <= rpgp_mvm_sym_distance_bound() and max r2 <= 10x that.  Statistics written by the operand
+ * pre-pass decide per call on the device; beyond the bound the direct-difference kernel runs (no host synchronisation either way).  rpgp_mvm_sym_distance_plan reports the chunking of that path:
  * plan = {supported, groups per chunk, k-steps of 8 per group, 128-byte operand lines per row, chunks}. */
 float rpgp_mvm_sym_distance_bound(void);
 int rpgp_mvm_sym_distance_plan(const rpgp_layout* lay, int plan[5]);

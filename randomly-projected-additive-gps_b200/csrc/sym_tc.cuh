@@ -13,6 +13,11 @@ struct TcdPlan {
 TcdPlan plan_tcd(const Layout& lay);
 size_t tcd_workspace_bytes(long long n, const Layout& lay);   // gate word + A / B operand images (0 when unsupported)
 float tcd_gate_bound();
+struct TcdGate {
+    unsigned max_bits;   // bits of the largest admissible squared group norm of a single row
+    double sum4_max;     // largest admissible sum over (row, group) of the squared squared norms
+};
+TcdGate tcd_gate(long long n, const Layout& lay);
 // builds the operand images and launches the kernel on the unique block pairs of row blocks [rb_begin, rb_begin + nrb);
 // *gate_out points at the device word the direct-difference kernel must consult (it runs only when the word exceeds the bound)
 int launch_sym_tcd(const float* zp, long long n, const Layout& lay, const float* nlc, const float* bsplit, double* acc, int nblocks,

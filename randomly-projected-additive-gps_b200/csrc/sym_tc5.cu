@@ -75,7 +75,8 @@ struct Sym5Args {
     const float* nlc;      // [nchunks][CP or G]
     double* acc;           // [n][16] FP64 accumulators (zeroed by the launcher)
     const unsigned* gate;  // K > 1 only: bits of max |z_group|^2 written by sym_tcd.cu's pre-pass (NULL: always run)
-    unsigned gate_min;     // run only when *gate > gate_min (below, the distance-on-tensor-core kernel has taken the launch)
+    unsigned gate_max;     // run only when the gate is closed (tcd_gate_open false); otherwise the distance-on-tensor-core kernel
+    double gate_sum4_max;  // has taken the launch
     long long n;
     int nblocks, half, nsplits, rb_begin;
 };
@@ -89,7 +90,7 @@ __global__ void __launch_bounds__(128 * HALVES + 128, 2) mvm_sym_tc5_kernel(cons
     constexpr int AW = 4 * HALVES;                 // arithmetic warps
     constexpr int FC = T5_N / HALVES;              // right-hand-side columns folded by one arithmetic warp
     constexpr int REGS_ARITH = HALVES == 1 ? T5_REGS_ARITH : 96, REGS_HELP = HALVES == 1 ? T5_REGS_HELP : 48;
-    if (KP > 1 && a.gate != nullptr && *a.gate <= a.gate_min) return;
+    if (KP > 1 && a.gate != nullptr && tcd_gate_open(a.gate, a.gate_max, a.gate_sum4_max)) return;
     extern __shared__ unsigned char smem_raw[];
     const uint32_t base = (smem_u32(smem_raw) + 1023u) & ~1023u;
     unsigned char* sm = smem_raw + (base - smem_u32(smem_raw));
@@ -392,7 +393,7 @@ int launch_sym_tc5(const float* zp, long long n, const Layout& lay, const float*
         RPGP_CUDA_OK(cudaGetLastError());
         Sym5Args a;
         a.z = zp; a.bsplit = bsplit; a.nlc = nlc; a.acc = acc; a.n = n;
-        a.gate = nullptr; a.gate_min = 0;
+        a.gate = nullptr; a.gate_max = 0; a.gate_sum4_max = 0.0;
         a.nblocks = nblocks;
         a.half = nblocks / 2 + 1;
         a.rb_begin = rb_begin;
@@ -429,8 +430,9 @@ int launch_sym_tc5(const float* zp, long long n, const Layout& lay, const float*
                                              workspace_bytes - base_bytes, &gate, st))
                     return rcd;
                 a.gate = gate;
-                const float bound = tcd_gate_bound();
-                memcpy(&a.gate_min, &bound, sizeof(float));
+                const TcdGate gb = tcd_gate(n, lay);
+                a.gate_max = gb.max_bits;
+                a.gate_sum4_max = gb.sum4_max;
             }
             // K > 1: the (KP, G, CP) chunk shapes of dispatch.cuh; one MUFU per group, so no polynomial offload; two threads per row
 #define RPGP_SYM5_KN(KPv, Gv, CPv, TPv) if (KP == KPv && G == Gv && CP == CPv) rc = run_sym5<CPv, KPv, Gv, 0, 2>(a, grid, st);

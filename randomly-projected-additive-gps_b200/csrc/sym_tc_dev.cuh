@@ -92,5 +92,11 @@ struct Tile5Iter {
     __device__ __forceinline__ int next_live(int t) const { while (t < ntiles && !live(t)) ++t; return t; }
 };
 
+// gate of the distance-on-tensor-core path: words written by its pre-pass = {bits of max r2, -, double sum of r2^2} where r2 is
+// the centred, scaled squared norm of a (row, group).  Both symmetric kernels evaluate it: exactly one of them runs.
+__device__ __forceinline__ bool tcd_gate_open(const unsigned* gate, unsigned max_bits, double sum4_max) {
+    return gate[0] <= max_bits && *reinterpret_cast<const double*>(gate + 2) <= sum4_max;
+}
+
 }  // namespace tcdev
 }  // namespace rpgp
