@@ -2,7 +2,9 @@
 
 Prediction restates DefaultPredictionStrategy: mean cache = K^-1 (y - mu) by CG with
 eval_cg_tolerance (one square multi-iteration solve, t = 1), predictive mean = K(X*, X) mean_cache + mu (one rectangular
-K.V), covariance = K** - K*X K^-1 KX* (n* right-hand sides) unless settings.skip_posterior_variances.
+K.V), covariance = K** - K*X K^-1 KX* (n* right-hand sides) unless settings.skip_posterior_variances.  Small problems form
+the covariance densely; beyond settings.max_dense_predictive_size, or under settings.fast_pred_var (LOVE: cached Lanczos root of
+K^-1, gp_experiment_runner.py:235,327), it stays lazy (rpgp/lazy.py PredictiveCovarLazyTensor) and variances come out in batches.
 """
 import torch
 
@@ -22,6 +24,7 @@ class ExactGP(Module):
         self.train_targets = train_targets
         self.likelihood = likelihood
         self._mean_cache = None
+        self._love_root = None
 
     def _apply(self, fn):
         if self.train_inputs is not None:
@@ -32,6 +35,7 @@ class ExactGP(Module):
     def train(self, mode=True):
         if mode:
             self._mean_cache = None
+            self._love_root = None
         return super().train(mode)
 
     def set_train_data(self, inputs=None, targets=None, strict=True):
@@ -42,6 +46,7 @@ class ExactGP(Module):
         if targets is not None:
             self.train_targets = targets
         self._mean_cache = None
+        self._love_root = None
 
     def __call__(self, *args, **kwargs):
         inputs = [a.unsqueeze(-1) if a.dim() == 1 else a for a in args]
@@ -70,6 +75,21 @@ class ExactGP(Module):
         n_test = x_test.shape[-2]
         if settings.skip_posterior_variances.on():
             covar = lazy.ZeroLazyTensor(n_test, n_test, dtype=pred_mean.dtype, device=pred_mean.device)
+            return MultivariateNormal(pred_mean, covar)
+        lazy_cov = settings.fast_pred_var.on() or n_test * x_train.shape[-2] > settings.max_dense_predictive_size.value()
+        if lazy_cov and isinstance(cross, lazy.RPAdditiveLazyTensor):
+            with torch.no_grad():
+                root = None
+                if settings.fast_pred_var.on():     # LOVE: Lanczos root of K^-1 started from the mean cross-covariance column
+                    if self._love_root is None:
+                        from ..solver.lanczos import lanczos_root_inv
+                        ones = torch.full((n_test, 1), 1.0 / n_test, dtype=pred_mean.dtype, device=pred_mean.device)
+                        init = cross._transpose_nonbatch()._matmul(ones)
+                        rank = min(settings.max_root_decomposition_size.value(), x_train.shape[-2])
+                        self._love_root = lanczos_root_inv(self._train_covar._matmul, init, rank)
+                    root = self._love_root
+                test_test = self.covar_module(x_test).evaluate_kernel()
+                covar = lazy.PredictiveCovarLazyTensor(test_test.detach(), cross.detach(), self._train_covar, root=root)
             return MultivariateNormal(pred_mean, covar)
         with torch.no_grad():
             cross_dense = cross.evaluate().detach()                                    # n* x n

@@ -95,6 +95,22 @@ class checkpoint_kernel(_Value):
     _default = 0
 
 
+class max_root_decomposition_size(_Value):
+    """rank of the Lanczos root of K^-1 that fast_pred_var (LOVE) caches; gpytorch default 100"""
+    _default = 100
+
+
+class max_dense_predictive_size(_Value):
+    """n* x n entries up to which the predictive covariance is formed densely (exact, what gpytorch's default strategy
+    does); above it -- or under fast_pred_var -- the covariance stays lazy (rpgp/lazy.py PredictiveCovarLazyTensor)"""
+    _default = 1 << 25
+
+
+class variance_batch_size(_Value):
+    """test points per multi-right-hand-side solve when exact predictive variances are computed lazily"""
+    _default = 64
+
+
 class skip_posterior_variances(_Flag):
     _default = False
 

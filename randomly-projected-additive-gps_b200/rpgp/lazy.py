@@ -325,6 +325,78 @@ class ZeroLazyTensor(LazyTensor):
         return DenseLazyTensor(torch.diag_embed(diag.reshape(-1).expand(self._sizes[0]).to(self._dtype)))
 
 
+class PredictiveCovarLazyTensor(LazyTensor):
+    """K** - K*X A KX*, the exact-GP predictive covariance kept lazy (gpytorch DefaultPredictionStrategy.exact_predictive_covar;
+    reached from training_routines.py:551-575).  A is K^-1 applied by multi-right-hand-side CG (exact), or, under
+    settings.fast_pred_var, the cached Lanczos root W W^T ~= K^-1 (LOVE; gp_experiment_runner.py:235,327).  Nothing of
+    size n x n* is ever formed: `diag()` works through the test points in batches, `_matmul` costs one solve (exact) or two
+    thin products (LOVE)."""
+
+    def __init__(self, test_test, cross, train_covar, root=None):
+        self.test_test, self.cross, self.train_covar = test_test, cross, train_covar
+        self.root = root                      # n x r, K^-1 ~= root root^T
+        self._cross_root = None               # n* x r = K*X root
+
+    dtype = property(lambda self: self.cross.dtype)
+    device = property(lambda self: self.cross.device)
+
+    def _size(self):
+        m = self.cross.shape[0]
+        return torch.Size((m, m))
+
+    def _transpose_nonbatch(self):
+        return self
+
+    def _cross_times_root(self):
+        if self._cross_root is None:
+            self._cross_root = self.cross._matmul(self.root)
+        return self._cross_root
+
+    def _matmul(self, rhs):
+        squeeze = rhs.dim() == 1
+        V = rhs.unsqueeze(-1) if squeeze else rhs
+        out = self.test_test._matmul(V)
+        if self.root is not None:
+            cr = self._cross_times_root()
+            out = out - cr @ (cr.t() @ V)
+        else:
+            out = out - self.cross._matmul(self.train_covar.inv_matmul(self.cross._transpose_nonbatch()._matmul(V)))
+        return out.squeeze(-1) if squeeze else out
+
+    matmul = _matmul
+
+    def rows(self, index):
+        index = torch.as_tensor(index, device=self.device).reshape(-1)
+        out = self.test_test.rows(index)
+        if self.root is not None:
+            cr = self._cross_times_root()
+            return out - cr[index] @ cr.t()
+        c_rows = self.cross.rows(index)                                    # b x n
+        solves = self.train_covar.inv_matmul(c_rows.t().contiguous())       # n x b
+        return out - self.cross._matmul(solves).t()
+
+    def diag(self):
+        prior = self.test_test.diag()
+        if self.root is not None:
+            cr = self._cross_times_root()
+            return prior - (cr * cr).sum(-1)
+        m = self.cross.shape[0]
+        out = torch.empty(m, dtype=self.dtype, device=self.device)
+        step = max(1, int(_settings().variance_batch_size.value()))
+        for i0 in range(0, m, step):
+            idx = torch.arange(i0, min(m, i0 + step), device=self.device)
+            c_rows = self.cross.rows(idx)                                   # b x n   (K(X*_b, X))
+            solves = self.train_covar.inv_matmul(c_rows.t().contiguous())   # n x b   (one multi-RHS CG solve)
+            out[idx] = prior[idx] - (c_rows.t() * solves).sum(0)
+        return out
+
+    _approx_diag = diag
+
+    def evaluate(self):
+        m = self.cross.shape[0]
+        return self._matmul(torch.eye(m, dtype=self.dtype, device=self.device))
+
+
 class AddedDiagLazyTensor(LazyTensor):
     """K + sigma^2 I: the operator CG actually solves with (GaussianLikelihood adds the noise, never the kernel)."""
 
@@ -340,12 +412,6 @@ class AddedDiagLazyTensor(LazyTensor):
     def _size(self):
         return self.base._size()
 
-    def representation(self):
-        return tuple(self.base.representation()) + (self.noise,)
-
-    def _rebuild(self, *rep):
-        return AddedDiagLazyTensor(self.base._rebuild(*rep[:-1]), rep[-1])
-
     def _noise_scalar(self):
         return self.noise.reshape(-1)[0]
 
@@ -355,7 +421,19 @@ class AddedDiagLazyTensor(LazyTensor):
     def matmul(self, rhs):
         return self.base.matmul(rhs) + self._noise_scalar() * rhs
 
+    def representation(self):
+        if isinstance(self.base, PredictiveCovarLazyTensor):
+            return (self.noise,)
+        return tuple(self.base.representation()) + (self.noise,)
+
+    def _rebuild(self, *rep):
+        if isinstance(self.base, PredictiveCovarLazyTensor):
+            return AddedDiagLazyTensor(self.base, rep[-1])
+        return AddedDiagLazyTensor(self.base._rebuild(*rep[:-1]), rep[-1])
+
     def _quad_form_derivative(self, left_vecs, right_vecs):
+        if isinstance(self.base, PredictiveCovarLazyTensor):      # evaluation only: no hyper-parameter gradients through it
+            return ((left_vecs * right_vecs).sum().reshape(self.noise.shape).to(self.noise.dtype),)
         base = self.base._quad_form_derivative(left_vecs, right_vecs)
         dnoise = (left_vecs * right_vecs).sum().reshape(self.noise.shape).to(self.noise.dtype)
         return tuple(base) + (dnoise,)

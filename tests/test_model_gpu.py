@@ -273,6 +273,76 @@ def test_prediction_matches_dense_oracle(n, tol):
     assert rel(out2.mean.cpu().numpy(), ref_mean) < tol and float(out2.variance.max()) <= 1e-9
 
 
+def _dense_prediction(model, X, Xt, y):
+    m = copy.deepcopy(model).to("cpu", torch.float64)
+    opx = m.covar_module(X.cpu().double()).evaluate_kernel()
+    opt = m.covar_module(Xt.cpu().double(), X.cpu().double()).evaluate_kernel()
+    return orc.predict_dense(opx.Z1.detach().numpy(), opt.Z1.detach().numpy(), opx.c.detach().numpy(), opx.J, opx.K,
+                             m.likelihood.noise.item(), y.cpu().numpy().astype(np.float64), m.mean_module.constant.item())
+
+
+def test_lazy_predictive_variances_match_dense_oracle():
+    """predictive variances without the n* x n cross-covariance -- batches of test points, one multi-right-hand-side
+    CG solve each (through the symmetric tensor-core kernel), against the dense FP64 oracle; then the joint test log-probability
+    (`test_nll` of train_exact_gp, training_routines.py:567) through the same lazy covariance."""
+    n, nt = 1500, 130
+    X, y = synthetic(n, 6, seed=14)
+    Xt, yt = synthetic(nt, 6, seed=15)
+    model, lik, mll = build("additive_rp_J20_K1", X, y)
+    perturb(model, 2)
+    model.eval()
+    lik.eval()
+    ref_mean, ref_var = _dense_prediction(model, X, Xt, y)
+    with torch.no_grad(), settings.eval_cg_tolerance(1e-6), settings.max_cg_iterations(4000), settings.max_dense_predictive_size(0), \
+            settings.variance_batch_size(48), warnings.catch_warnings():
+        warnings.simplefilter("ignore")
+        out = model(Xt)
+        from rpgp.lazy import PredictiveCovarLazyTensor
+        assert isinstance(out.lazy_covariance_matrix, PredictiveCovarLazyTensor)
+        var = out.variance.cpu().numpy()
+        lazy_dense = out.lazy_covariance_matrix.evaluate().cpu().numpy()
+        nll_lazy = -float(lik(out).log_prob(yt)) / nt
+    with torch.no_grad(), settings.eval_cg_tolerance(1e-6), settings.max_cg_iterations(4000), warnings.catch_warnings():
+        warnings.simplefilter("ignore")
+        out_dense = model(Xt)
+        nll_dense = -float(lik(out_dense).log_prob(yt)) / nt
+    assert rel(out.mean.cpu().numpy(), ref_mean) < 2e-3
+    assert rel(var, ref_var) < 2e-3, rel(var, ref_var)
+    assert rel(np.diag(lazy_dense), ref_var) < 2e-3
+    assert rel(lazy_dense, out_dense.covariance_matrix.cpu().numpy()) < 2e-3
+    assert abs(nll_lazy - nll_dense) < 1e-3 * max(1.0, abs(nll_dense)), (nll_lazy, nll_dense)
+
+
+def test_love_fast_predictive_variances():
+    """settings.fast_pred_var (gp_experiment_runner.py:235,327): cached Lanczos root of K^-1.  At full rank it reproduces the exact
+    variances; at the default-style low rank it stays an upper bound of them (the root under-estimates K^-1) within a few percent
+    of the prior variance."""
+    n, nt = 700, 90
+    X, y = synthetic(n, 6, seed=24)
+    Xt, _ = synthetic(nt, 6, seed=25)
+    model, lik, mll = build("additive_rp_J20_K1", X, y)
+    perturb(model, 3)
+    model.eval()
+    lik.eval()
+    _, ref_var = _dense_prediction(model, X, Xt, y)
+    prior_var = float(model.covar_module(Xt).evaluate_kernel().diag().detach().max())
+    with torch.no_grad(), settings.fast_pred_var(True), settings.max_root_decomposition_size(n), settings.eval_cg_tolerance(1e-6), \
+            warnings.catch_warnings():
+        warnings.simplefilter("ignore")
+        full = model(Xt).variance.cpu().numpy()
+    assert rel(full, ref_var) < 5e-3, rel(full, ref_var)
+    model.train()
+    model.eval()
+    with torch.no_grad(), settings.fast_pred_var(True), settings.max_root_decomposition_size(100), settings.eval_cg_tolerance(1e-6), \
+            warnings.catch_warnings():
+        warnings.simplefilter("ignore")
+        out = model(Xt)
+        low = out.variance.cpu().numpy()
+        assert out.lazy_covariance_matrix.root.shape[1] <= 100
+    assert np.all(low > ref_var - 1e-3 * prior_var)
+    assert np.abs(low - ref_var).max() < 0.25 * prior_var
+
+
 def test_one_adam_step_moves_the_right_parameters():
     # test.py:575-621: lengthscale moves, frozen base lengthscale and W stay; with learn_proj W moves too
     x = torch.tensor([[1., 2., 3.], [1.1, 2.2, 3.3]], device=DEV)
