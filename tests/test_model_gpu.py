@@ -5,6 +5,7 @@ gradients and predictions -- which no reference test pins -- are checked against
 the tolerances of BASELINE.json (MLL / gradients 1e-4 relative on the exact path; trained-model predictions 1 %).
 """
 import copy
+import json
 import math
 import os
 import warnings
@@ -402,3 +403,29 @@ def test_train_exact_gp_end_to_end_cfg1_shape():
     ref_nll = 0.5 * (sol @ sol + 2 * np.log(np.diag(Lc)).sum() + nt * math.log(2 * math.pi))
     ref_nll = (ref_nll - orc.smoothed_box_log_prob(m.likelihood.noise.item())) / nt
     assert abs(metrics["test_nll"] - ref_nll) / abs(ref_nll) < 0.01, (metrics["test_nll"], ref_nll)
+
+
+def test_experiment_runner_end_to_end(tmp_path):
+    """the reference's UCI protocol through gp_experiment_runner.main -- spec file, fold split, train-set
+    normalisation, solver flags (with --fast_pred: LOVE variances), train_exact_gp on the fused kernels, CSV on disk."""
+    import gp_experiment_runner as runner
+    X, y = synthetic(900, 5, seed=31, device="cpu")
+    frame = runner.frame_from_array(np.concatenate([X.numpy(), y.numpy()[:, None]], axis=1))
+    spec = tr.load_model_spec("additive_rp_J20_K1")
+    spec["train_kwargs"].update(max_iter=12, check_conv=False)
+    spec_path, out = tmp_path / "spec.json", tmp_path / "res.csv"
+    spec_path.write_text(json.dumps(spec))
+    torch.manual_seed(5)
+    np.random.seed(5)
+    with warnings.catch_warnings():
+        warnings.simplefilter("ignore")
+        table = runner.main(["-m", str(spec_path), "-d", "synthetic", "-o", str(out), "-s", "0.2", "--no_cv", "--fold", "2",
+                             "--cg_tol", "0.01", "--eval_cg_tol", "0.001", "--fast_pred", "--skip_random_restart", "--device", "cuda:0",
+                             "--error_repeats", "1"], datasets_override={"synthetic": frame})
+    assert len(table) == 1 and "error" not in table.columns, table.get("error")
+    row = table.iloc[0]
+    assert row["fold"] == 2 and row["n"] == 900 and row["d"] == 5 and row["trained_epochs"] == 12
+    assert np.isfinite(row["rmse"]) and row["rmse"] < 0.6 and np.isfinite(row["test_nll"]) and 0.3 < row["test_pred_frac_in_cr"] <= 1.0
+    import pandas as pd
+    saved = pd.read_csv(out)
+    assert bool(saved["fast_pred_var"][0]) and saved["dataset"][0] == "synthetic" and abs(saved["cg_tol"][0] - 0.01) < 1e-12
