@@ -53,7 +53,14 @@ typedef struct {
     int nchunks;   /* coordinate chunks */
     int KP;        /* padded coordinates per group (1 when K == 1) */
     int G;         /* groups per chunk */
+    int base;      /* base kernel of every group (rpgp_base_kernel); rpgp_plan_layout sets RBF */
 } rpgp_layout;
+
+/* base kernels k(d^2) of a projection group (training_routines.py:57-83 `_map_to_kernel`; gp_models/kernels/imq_kernel.py:8-9,47):
+ *   RBF exp(-d^2/2);  Matern nu=1.5 (1 + sqrt3 d) exp(-sqrt3 d);  inverse multiquadric (d^2 + 1)^-1/2.
+ * The non-RBF kernels run on the SIMT forward / gradient kernels with the group layouts (K = 1 is stored with KP = 2); the
+ * symmetric tensor-core kernels are RBF only (rpgp_mvm_sym_supported returns 0). */
+typedef enum { RPGP_BASE_RBF = 0, RPGP_BASE_MATERN15 = 1, RPGP_BASE_INVERSE_MQ = 2 } rpgp_base_kernel;
 
 int rpgp_version(void);
 const char* rpgp_last_error(void);
@@ -62,6 +69,7 @@ unsigned long long rpgp_launch_count(void);
 
 /* layout planning ------------------------------------------------------------------------------------------------ */
 int rpgp_plan_layout(int J, int K, rpgp_layout* out);
+int rpgp_plan_layout_base(int J, int K, int base, rpgp_layout* out);
 /* padded right-hand-side width TP the kernels are compiled for; 0 when t exceeds rpgp_max_rhs (chunk the columns) */
 int rpgp_padded_rhs(const rpgp_layout* lay, int t, int backward);
 int rpgp_max_rhs(const rpgp_layout* lay, int backward);
@@ -125,6 +133,16 @@ int rpgp_quad_bwd_f32(const float* z1p, int64_t m, int64_t z1_stride, const floa
 /* dense rows / blocks of K on natural (un-scaled) coordinates: out[p, i'] = K(Zr[p], Z2[i']); out: P x n */
 int rpgp_kernel_rows_f32(const float* Zr, int64_t P, const float* Z2, int64_t n, int64_t ld, int J, int K,
                          const float* c, float* out, int64_t ldo, void* stream);
+
+/* the natural-coordinate entry points (dense rows here, FP64 below) with an explicit base kernel; the plain names are RBF */
+int rpgp_kernel_rows_base_f32(const float* Zr, int64_t P, const float* Z2, int64_t n, int64_t ld, int J, int K, int base,
+                              const float* c, float* out, int64_t ldo, void* stream);
+int rpgp_kernel_rows_base_f64(const double* Zr, int64_t P, const double* Z2, int64_t n, int64_t ld, int J, int K, int base,
+                              const double* c, double* out, int64_t ldo, void* stream);
+int rpgp_mvm_fwd_base_f64(const double* Z1, int64_t m, const double* Z2, int64_t n, int64_t ld, int J, int K, int base,
+                          const double* c, const double* V, int t, double* out, void* stream);
+int rpgp_quad_bwd_base_f64(const double* Z1, int64_t m, const double* Z2, int64_t n, int64_t ld, int J, int K, int base,
+                           const double* c, const double* L, const double* R, int t, double* dZ1, double* g, void* stream);
 
 /* FP64 path (natural coordinates, small n): same semantics, un-tiled */
 int rpgp_mvm_fwd_f64(const double* Z1, int64_t m, const double* Z2, int64_t n, int64_t ld, int J, int K,

@@ -59,7 +59,29 @@ def scaled_projection(X, W, ell, prescale, dtype=np.float64):
 # restates AdditiveKernel(ScaleKernel(RBF(active_dims=group j)))  -- polynomial_projection_kernels.py:65-103,
 # training_routines.py:148-174 -- with RBF = exp(-1/2 |a-b|^2) (KeOps form, imq_kernel.py:44-47 analogue).
 # ----------------------------------------------------------------------------------------------
-def additive_rbf_dense(Z1, Z2, c, J, K, dtype=np.float64):
+# base kernels of a group as functions of its squared distance (training_routines.py:57-83 `_map_to_kernel`):
+#   0 RBF  exp(-sq/2)            gpytorch RBFKernel / keops RBFKernel
+#   1 Matern nu=1.5  (1 + sqrt(3 sq)) exp(-sqrt(3 sq))   gpytorch MaternKernel(nu=1.5) [GPyTorch, recalled]
+#   2 inverse multiquadric  (sq + 1)^-1/2   gp_models/kernels/imq_kernel.py:8-9 (postprocess_inverse_mq), :47 (KeOps form)
+def base_f(base, sq):
+    if base == 1:
+        q = np.sqrt(3.0 * sq)
+        return (1.0 + q) * np.exp(-q)
+    if base == 2:
+        return 1.0 / np.sqrt(sq + 1.0)
+    return np.exp(-0.5 * sq)
+
+
+def base_df(base, sq):
+    """d f / d sq"""
+    if base == 1:
+        return -1.5 * np.exp(-np.sqrt(3.0 * sq))
+    if base == 2:
+        return -0.5 * (sq + 1.0) ** -1.5
+    return -0.5 * np.exp(-0.5 * sq)
+
+
+def additive_rbf_dense(Z1, Z2, c, J, K, dtype=np.float64, base=0):
     Z1 = np.asarray(Z1, dtype=dtype)
     Z2 = np.asarray(Z2, dtype=dtype)
     c = np.broadcast_to(np.asarray(c, dtype=dtype), (J,))
@@ -70,11 +92,11 @@ def additive_rbf_dense(Z1, Z2, c, J, K, dtype=np.float64):
         for q in range(j * K, (j + 1) * K):
             diff = Z1[:, q][:, None] - Z2[:, q][None, :]
             sq += diff * diff
-        out += c[j] * np.exp(-0.5 * sq)
+        out += c[j] * base_f(base, sq)
     return out
 
 
-def kmv(Z1, Z2, c, J, K, V, diag_add=0.0, row_chunk=1024, dtype=np.float64):
+def kmv(Z1, Z2, c, J, K, V, diag_add=0.0, row_chunk=1024, dtype=np.float64, base=0):
     """out = K(Z1,Z2) @ V (+ diag_add * V when square); row-chunked like gpytorch checkpoint_kernel
     (gp_experiment_runner.py:250,330) so that K is never held whole."""
     Z1 = np.asarray(Z1, dtype=dtype)
@@ -82,7 +104,7 @@ def kmv(Z1, Z2, c, J, K, V, diag_add=0.0, row_chunk=1024, dtype=np.float64):
     out = np.empty((Z1.shape[0], V.shape[1]), dtype=dtype)
     for r0 in range(0, Z1.shape[0], row_chunk):
         r1 = min(r0 + row_chunk, Z1.shape[0])
-        out[r0:r1] = additive_rbf_dense(Z1[r0:r1], Z2, c, J, K, dtype=dtype) @ V
+        out[r0:r1] = additive_rbf_dense(Z1[r0:r1], Z2, c, J, K, dtype=dtype, base=base) @ V
     if diag_add != 0.0:
         out += diag_add * V
     return out
@@ -102,7 +124,7 @@ def kernel_diag(c, J, n, dtype=np.float64):
 # quadratic-form derivative:  G = sum_col L[:,col]^T K R[:,col]
 # explicit per-pair formulas, the analogue of GAMFunction.backward memory_efficient_gam_kernel.py:33-59
 # ----------------------------------------------------------------------------------------------
-def quad_form_grads(Z1, Z2, c, J, K, L, R, dtype=np.float64):
+def quad_form_grads(Z1, Z2, c, J, K, L, R, dtype=np.float64, base=0):
     """Return (dG/dZ1, dG/dZ2, dG/dc) with Z1, Z2 treated as independent tensors."""
     Z1 = np.asarray(Z1, dtype=dtype)
     Z2 = np.asarray(Z2, dtype=dtype)
@@ -120,9 +142,8 @@ def quad_form_grads(Z1, Z2, c, J, K, L, R, dtype=np.float64):
             diff = Z1[:, q][:, None] - Z2[:, q][None, :]
             diffs.append(diff)
             sq += diff * diff
-        e = np.exp(-0.5 * sq)
-        dc[j] = (S * e).sum()
-        w = S * e * c[j]
+        dc[j] = (S * base_f(base, sq)).sum()
+        w = -2.0 * S * base_df(base, sq) * c[j]                  # RBF: S k c
         for mm, q in enumerate(range(j * K, (j + 1) * K)):
             wd = w * diffs[mm]
             dZ1[:, q] = -wd.sum(axis=1)

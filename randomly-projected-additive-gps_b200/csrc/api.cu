@@ -46,8 +46,13 @@ static int check_layout(const rpgp_layout* lay) {
     RPGP_REQUIRE(lay->nchunks >= 1 && lay->G >= 1 && lay->KP >= 1, "layout: nchunks/G/KP must be >= 1");
     RPGP_REQUIRE(lay->KP >= lay->K && lay->G * lay->KP <= lay->CP, "layout: group shape KP=%d G=%d exceeds CP=%d", lay->KP, lay->G, lay->CP);
     RPGP_REQUIRE((long long)lay->nchunks * lay->G >= lay->J, "layout: %d chunks x %d groups < J=%d", lay->nchunks, lay->G, lay->J);
-    RPGP_REQUIRE((lay->K == 1) == (lay->KP == 1), "layout: KP must be 1 exactly when K is 1");
-    RPGP_REQUIRE(lay->K > 1 || lay->G == lay->CP, "layout: K=1 requires G == CP");
+    RPGP_REQUIRE(lay->base >= 0 && lay->base <= 2, "layout: base kernel %d (0 RBF, 1 Matern-1.5, 2 inverse multiquadric)", lay->base);
+    if (lay->base == 0) {
+        RPGP_REQUIRE((lay->K == 1) == (lay->KP == 1), "layout: KP must be 1 exactly when K is 1");
+    } else {
+        RPGP_REQUIRE(lay->KP >= 2, "layout: non-RBF base kernels use the group layouts (KP >= 2)");
+    }
+    RPGP_REQUIRE(lay->KP > 1 || lay->G == lay->CP, "layout: K=1 requires G == CP");
     return OK;
 }
 
@@ -67,7 +72,7 @@ unsigned long long rpgp_launch_count(void) { return rpgp::launch_count(); }
 // TP actually compiled for (layout, t): forward K=1 {4,8,12,16,32}; backward K=1 {4,12,16}; K>1 {4,16}
 int rpgp_padded_rhs(const rpgp_layout* lay, int t, int backward) {
     if (!lay || t <= 0) return 0;
-    if (lay->K > 1) return t <= 4 ? 4 : (t <= 16 ? 16 : 0);
+    if (lay->KP > 1) return t <= 4 ? 4 : (t <= 16 ? 16 : 0);
     if (backward) return t <= 4 ? 4 : (t <= 12 ? 12 : (t <= 16 ? 16 : 0));
     if (t <= 4) return 4;
     if (t <= 8) return 8;
@@ -76,14 +81,18 @@ int rpgp_padded_rhs(const rpgp_layout* lay, int t, int backward) {
     if (t <= 32) return 32;
     return 0;
 }
-int rpgp_max_rhs(const rpgp_layout* lay, int backward) { return (lay && lay->K == 1 && !backward) ? 32 : 16; }
+int rpgp_max_rhs(const rpgp_layout* lay, int backward) { return (lay && lay->KP == 1 && !backward) ? 32 : 16; }
 
-int rpgp_plan_layout(int J, int K, rpgp_layout* out) {
+int rpgp_plan_layout(int J, int K, rpgp_layout* out) { return rpgp_plan_layout_base(J, K, 0, out); }
+
+int rpgp_plan_layout_base(int J, int K, int base, rpgp_layout* out) {
     RPGP_REQUIRE(out != nullptr, "plan_layout: out is NULL");
     RPGP_REQUIRE(J >= 1 && K >= 1, "plan_layout: J=%d K=%d must be >= 1", J, K);
+    RPGP_REQUIRE(base >= 0 && base <= 2, "plan_layout: base kernel %d (0 RBF, 1 Matern-1.5, 2 inverse multiquadric)", base);
     out->J = J;
     out->K = K;
-    if (K == 1) {
+    out->base = base;
+    if (K == 1 && base == 0) {
         out->KP = 1;
         out->nchunks = (J + 31) / 32;
         const int per = (J + out->nchunks - 1) / out->nchunks;
@@ -183,10 +192,10 @@ int rpgp_mvm_fwd_f32(const float* z1p, int64_t m, int64_t z1_stride, const float
     dim3 grid((unsigned)sp.row_blocks, (unsigned)sp.nsplits, (unsigned)lay->nchunks);
     // RPGP_POLY_PAIRS overrides the number of projection pairs evaluated on the FMA pipe (tools/poly_sweep.py); -1 = default
     static const int poly_env = [] { const char* e = getenv("RPGP_POLY_PAIRS"); return e ? atoi(e) : -1; }();
-    const int poly_pairs = (lay->K == 1) ? (poly_env >= 0 ? poly_env : default_poly_pairs(lay->CP, TP)) : 0;
+    const int poly_pairs = (lay->KP == 1) ? (poly_env >= 0 ? poly_env : default_poly_pairs(lay->CP, TP)) : 0;
     int rc;
-    if (lay->K == 1 && poly_pairs > 0) rc = launch_fwd_k1_poly(lay->CP, TP, poly_pairs, a, grid, st);
-    else rc = (lay->K == 1) ? launch_fwd_k1(lay->CP, TP, a, grid, st) : launch_fwd_kn(lay->KP, lay->G, lay->CP, TP, a, grid, st);
+    if (lay->KP == 1 && poly_pairs > 0) rc = launch_fwd_k1_poly(lay->CP, TP, poly_pairs, a, grid, st);
+    else rc = (lay->KP == 1) ? launch_fwd_k1(lay->CP, TP, a, grid, st) : launch_fwd_kn(lay->KP, lay->G, lay->CP, TP, lay->base, a, grid, st);
     if (rc) return rc;
     if (!a.direct) return launch_reduce_partials(a.partial, (int)nparts, m, TP, t, out, ldo, st);
     return OK;
@@ -208,7 +217,7 @@ int rpgp_mvm_sym_distance_plan(const rpgp_layout* lay, int plan[5]) {
 }
 
 int rpgp_mvm_sym_supported(const rpgp_layout* lay, int t) {
-    return lay && check_layout(lay) == OK && t >= 1 && t <= 16;
+    return lay && check_layout(lay) == OK && lay->base == 0 && t >= 1 && t <= 16;     // the tensor-core kernels are RBF
 }
 
 int rpgp_mvm_sym_f32(const float* zp, int64_t n, const rpgp_layout* lay, const float* neg_log2c, const float* Vp16, int t,
@@ -268,7 +277,7 @@ int rpgp_quad_bwd_f32(const float* z1p, int64_t m, int64_t z1_stride, const floa
     a.m = m; a.n = n; a.z1_chunk_stride = z1_stride; a.z2_chunk_stride = z2_stride;
     a.cols_per_split = sp.cols_per_split; a.nsplits = sp.nsplits; a.nchunks = lay->nchunks; a.symmetric = symmetric ? 1 : 0;
     dim3 grid((unsigned)sp.row_blocks, (unsigned)sp.nsplits, (unsigned)lay->nchunks);
-    int rc = (lay->K == 1) ? launch_grad_k1(lay->CP, TPk, a, grid, st) : launch_grad_kn(lay->KP, lay->G, lay->CP, TPk, a, grid, st);
+    int rc = (lay->KP == 1) ? launch_grad_k1(lay->CP, TPk, a, grid, st) : launch_grad_kn(lay->KP, lay->G, lay->CP, TPk, lay->base, a, grid, st);
     if (rc) return rc;
     // d k / d z1 = k * ln2 * (-2 d)  in scaled coordinates
     const float dz_scale = (float)(-2.0 * LN2_D);
@@ -278,31 +287,51 @@ int rpgp_quad_bwd_f32(const float* z1p, int64_t m, int64_t z1_stride, const floa
     return launch_reduce_g(a.g_partial, sp.row_blocks * sp.nsplits, width, symmetric ? 0.5f : 1.0f, g, st);
 }
 
+int rpgp_kernel_rows_base_f32(const float* Zr, int64_t P, const float* Z2, int64_t n, int64_t ld, int J, int K, int base,
+                              const float* c, float* out, int64_t ldo, void* stream) {
+    RPGP_REQUIRE(P >= 0 && n >= 0 && J >= 1 && K >= 1 && ld >= (int64_t)J * K && ldo >= n, "kernel_rows: bad shape");
+    RPGP_REQUIRE(base >= 0 && base <= 2, "kernel_rows: base kernel %d", base);
+    RPGP_REQUIRE((P == 0 || n == 0) || (Zr && Z2 && c && out), "kernel_rows: NULL pointer");
+    return launch_rows_f32(Zr, P, Z2, n, ld, J, K, base, c, out, ldo, (cudaStream_t)stream);
+}
+int rpgp_kernel_rows_base_f64(const double* Zr, int64_t P, const double* Z2, int64_t n, int64_t ld, int J, int K, int base,
+                              const double* c, double* out, int64_t ldo, void* stream) {
+    RPGP_REQUIRE(P >= 0 && n >= 0 && J >= 1 && K >= 1 && ld >= (int64_t)J * K && ldo >= n, "kernel_rows: bad shape");
+    RPGP_REQUIRE(base >= 0 && base <= 2, "kernel_rows: base kernel %d", base);
+    RPGP_REQUIRE((P == 0 || n == 0) || (Zr && Z2 && c && out), "kernel_rows: NULL pointer");
+    return launch_rows_f64(Zr, P, Z2, n, ld, J, K, base, c, out, ldo, (cudaStream_t)stream);
+}
 int rpgp_kernel_rows_f32(const float* Zr, int64_t P, const float* Z2, int64_t n, int64_t ld, int J, int K,
                          const float* c, float* out, int64_t ldo, void* stream) {
-    RPGP_REQUIRE(P >= 0 && n >= 0 && J >= 1 && K >= 1 && ld >= (int64_t)J * K && ldo >= n, "kernel_rows: bad shape");
-    RPGP_REQUIRE((P == 0 || n == 0) || (Zr && Z2 && c && out), "kernel_rows: NULL pointer");
-    return launch_rows_f32(Zr, P, Z2, n, ld, J, K, c, out, ldo, (cudaStream_t)stream);
+    return rpgp_kernel_rows_base_f32(Zr, P, Z2, n, ld, J, K, 0, c, out, ldo, stream);
 }
 int rpgp_kernel_rows_f64(const double* Zr, int64_t P, const double* Z2, int64_t n, int64_t ld, int J, int K,
                          const double* c, double* out, int64_t ldo, void* stream) {
-    RPGP_REQUIRE(P >= 0 && n >= 0 && J >= 1 && K >= 1 && ld >= (int64_t)J * K && ldo >= n, "kernel_rows: bad shape");
-    RPGP_REQUIRE((P == 0 || n == 0) || (Zr && Z2 && c && out), "kernel_rows: NULL pointer");
-    return launch_rows_f64(Zr, P, Z2, n, ld, J, K, c, out, ldo, (cudaStream_t)stream);
+    return rpgp_kernel_rows_base_f64(Zr, P, Z2, n, ld, J, K, 0, c, out, ldo, stream);
 }
 
+int rpgp_mvm_fwd_base_f64(const double* Z1, int64_t m, const double* Z2, int64_t n, int64_t ld, int J, int K, int base,
+                          const double* c, const double* V, int t, double* out, void* stream) {
+    RPGP_REQUIRE(m >= 0 && n >= 0 && J >= 1 && K >= 1 && t >= 1 && ld >= (int64_t)J * K, "mvm_fwd_f64: bad shape");
+    RPGP_REQUIRE(base >= 0 && base <= 2, "mvm_fwd_f64: base kernel %d", base);
+    RPGP_REQUIRE(m == 0 || (Z1 && c && out && (n == 0 || (Z2 && V))), "mvm_fwd_f64: NULL pointer");
+    return launch_mvm_f64(Z1, m, Z2, n, ld, J, K, base, c, V, t, out, (cudaStream_t)stream);
+}
+int rpgp_quad_bwd_base_f64(const double* Z1, int64_t m, const double* Z2, int64_t n, int64_t ld, int J, int K, int base,
+                           const double* c, const double* L, const double* R, int t, double* dZ1, double* g, void* stream) {
+    RPGP_REQUIRE(m >= 0 && n >= 0 && J >= 1 && K >= 1 && t >= 1 && ld >= (int64_t)J * K, "quad_bwd_f64: bad shape");
+    RPGP_REQUIRE(base >= 0 && base <= 2, "quad_bwd_f64: base kernel %d", base);
+    RPGP_REQUIRE(m == 0 || n == 0 || (Z1 && Z2 && c && L && R && dZ1 && g), "quad_bwd_f64: NULL pointer");
+    if (n == 0) return OK;
+    return launch_quad_f64(Z1, m, Z2, n, ld, J, K, base, c, L, R, t, dZ1, g, (cudaStream_t)stream);
+}
 int rpgp_mvm_fwd_f64(const double* Z1, int64_t m, const double* Z2, int64_t n, int64_t ld, int J, int K,
                      const double* c, const double* V, int t, double* out, void* stream) {
-    RPGP_REQUIRE(m >= 0 && n >= 0 && J >= 1 && K >= 1 && t >= 1 && ld >= (int64_t)J * K, "mvm_fwd_f64: bad shape");
-    RPGP_REQUIRE(m == 0 || (Z1 && c && out && (n == 0 || (Z2 && V))), "mvm_fwd_f64: NULL pointer");
-    return launch_mvm_f64(Z1, m, Z2, n, ld, J, K, c, V, t, out, (cudaStream_t)stream);
+    return rpgp_mvm_fwd_base_f64(Z1, m, Z2, n, ld, J, K, 0, c, V, t, out, stream);
 }
 int rpgp_quad_bwd_f64(const double* Z1, int64_t m, const double* Z2, int64_t n, int64_t ld, int J, int K,
                       const double* c, const double* L, const double* R, int t, double* dZ1, double* g, void* stream) {
-    RPGP_REQUIRE(m >= 0 && n >= 0 && J >= 1 && K >= 1 && t >= 1 && ld >= (int64_t)J * K, "quad_bwd_f64: bad shape");
-    RPGP_REQUIRE(m == 0 || n == 0 || (Z1 && Z2 && c && L && R && dZ1 && g), "quad_bwd_f64: NULL pointer");
-    if (n == 0) return OK;
-    return launch_quad_f64(Z1, m, Z2, n, ld, J, K, c, L, R, t, dZ1, g, (cudaStream_t)stream);
+    return rpgp_quad_bwd_base_f64(Z1, m, Z2, n, ld, J, K, 0, c, L, R, t, dZ1, g, stream);
 }
 
 // ---- whole path on host buffers ---------------------------------------------------------------------------------------

@@ -74,10 +74,30 @@ __global__ void __launch_bounds__(256) project_kernel(const float* __restrict__ 
     }
 }
 
+// ---- base kernels on natural coordinates (sq = squared distance of a group): value f and slope df/dsq ---------------------
+template <typename T>
+__device__ __forceinline__ T base_f(int base, T sq) {
+    if (base == 1) {
+        const T q = sqrt(T(3) * sq);
+        return (T(1) + q) * exp(-q);
+    }
+    if (base == 2) return T(1) / sqrt(sq + T(1));
+    return exp(T(-0.5) * sq);
+}
+template <typename T>
+__device__ __forceinline__ T base_df(int base, T sq) {
+    if (base == 1) return T(-1.5) * exp(-sqrt(T(3) * sq));
+    if (base == 2) {
+        const T r = T(1) / sqrt(sq + T(1));
+        return T(-0.5) * r * r * r;
+    }
+    return T(-0.5) * exp(T(-0.5) * sq);
+}
+
 // ---- dense rows of K ------------------------------------------------------------------------------------------------
 template <typename T>
 __global__ void kernel_rows_kernel(const T* __restrict__ Zr, long long P, const T* __restrict__ Z2, long long n,
-                                   long long ld, int J, int K, const T* __restrict__ c, T* __restrict__ out,
+                                   long long ld, int J, int K, int base, const T* __restrict__ c, T* __restrict__ out,
                                    long long ldo) {
     const long long col = (long long)blockIdx.x * blockDim.x + threadIdx.x;
     const long long p = blockIdx.y;
@@ -91,7 +111,7 @@ __global__ void kernel_rows_kernel(const T* __restrict__ Zr, long long P, const 
             const T dd = a[j * K + mm] - b[j * K + mm];
             sq += dd * dd;
         }
-        s += c[j] * exp(T(-0.5) * sq);
+        s += c[j] * base_f<T>(base, sq);
     }
     out[p * ldo + col] = s;
 }
@@ -142,7 +162,7 @@ __global__ void reduce_g_kernel(const float* __restrict__ gp, long long nctas, i
 // ---- FP64 path (un-tiled; small n) ------------------------------------------------------------------------------------
 constexpr int F64_TMAX = 16;
 __global__ void mvm_fwd_f64_kernel(const double* __restrict__ Z1, long long m, const double* __restrict__ Z2,
-                                   long long n, long long ld, int J, int K, const double* __restrict__ c,
+                                   long long n, long long ld, int J, int K, int base, const double* __restrict__ c,
                                    const double* __restrict__ V, int t, int t0, int tc, double* __restrict__ out) {
     const long long row = (long long)blockIdx.x * blockDim.x + threadIdx.x;
     if (row >= m) return;
@@ -159,7 +179,7 @@ __global__ void mvm_fwd_f64_kernel(const double* __restrict__ Z1, long long m, c
                 const double dd = a[j * K + mm] - b[j * K + mm];
                 sq += dd * dd;
             }
-            s += c[j] * exp(-0.5 * sq);
+            s += c[j] * base_f<double>(base, sq);
         }
 #pragma unroll
         for (int q = 0; q < F64_TMAX; ++q)
@@ -172,7 +192,7 @@ __global__ void mvm_fwd_f64_kernel(const double* __restrict__ Z1, long long m, c
 
 // one thread per (row, j): accumulates dZ1[row, jK..jK+K) and atomically adds its share of g[j]
 __global__ void quad_bwd_f64_kernel(const double* __restrict__ Z1, long long m, const double* __restrict__ Z2,
-                                    long long n, long long ld, int J, int K, const double* __restrict__ c,
+                                    long long n, long long ld, int J, int K, int base, const double* __restrict__ c,
                                     const double* __restrict__ L, const double* __restrict__ R, int t,
                                     double* __restrict__ dZ1, double* __restrict__ g) {
     const long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x;
@@ -190,9 +210,9 @@ __global__ void quad_bwd_f64_kernel(const double* __restrict__ Z1, long long m, 
             const double dd = a[mm] - b[mm];
             sq += dd * dd;
         }
-        const double w = S * exp(-0.5 * sq) * c[j];
-        gsum += w;  // dG / d ln c_j
-        for (int mm = 0; mm < K; ++mm) dZ1[row * ld + (long long)j * K + mm] -= w * (a[mm] - b[mm]);
+        gsum += S * base_f<double>(base, sq) * c[j];  // dG / d ln c_j
+        const double w = 2.0 * S * base_df<double>(base, sq) * c[j];
+        for (int mm = 0; mm < K; ++mm) dZ1[row * ld + (long long)j * K + mm] += w * (a[mm] - b[mm]);
     }
     atomicAdd(g + j, gsum);
 }
@@ -234,24 +254,24 @@ int launch_project(const float* X, long long n, int d, long long ldx, const floa
     note_launch();
     return cuda_fail(cudaGetLastError(), "project_kernel");
 }
-int launch_rows_f32(const float* Zr, long long P, const float* Z2, long long n, long long ld, int J, int K,
+int launch_rows_f32(const float* Zr, long long P, const float* Z2, long long n, long long ld, int J, int K, int base,
                     const float* c, float* out, long long ldo, cudaStream_t st) {
     if (P == 0 || n == 0) return OK;
     for (long long p0 = 0; p0 < P; p0 += 32768) {
         const long long pc = (P - p0 < 32768) ? (P - p0) : 32768;
         dim3 grid((unsigned)((n + 255) / 256), (unsigned)pc);
-        kernel_rows_kernel<float><<<grid, 256, 0, st>>>(Zr + p0 * ld, pc, Z2, n, ld, J, K, c, out + p0 * ldo, ldo);
+        kernel_rows_kernel<float><<<grid, 256, 0, st>>>(Zr + p0 * ld, pc, Z2, n, ld, J, K, base, c, out + p0 * ldo, ldo);
     }
     note_launch();
     return cuda_fail(cudaGetLastError(), "kernel_rows_kernel<float>");
 }
-int launch_rows_f64(const double* Zr, long long P, const double* Z2, long long n, long long ld, int J, int K,
+int launch_rows_f64(const double* Zr, long long P, const double* Z2, long long n, long long ld, int J, int K, int base,
                     const double* c, double* out, long long ldo, cudaStream_t st) {
     if (P == 0 || n == 0) return OK;
     for (long long p0 = 0; p0 < P; p0 += 32768) {
         const long long pc = (P - p0 < 32768) ? (P - p0) : 32768;
         dim3 grid((unsigned)((n + 255) / 256), (unsigned)pc);
-        kernel_rows_kernel<double><<<grid, 256, 0, st>>>(Zr + p0 * ld, pc, Z2, n, ld, J, K, c, out + p0 * ldo, ldo);
+        kernel_rows_kernel<double><<<grid, 256, 0, st>>>(Zr + p0 * ld, pc, Z2, n, ld, J, K, base, c, out + p0 * ldo, ldo);
     }
     note_launch();
     return cuda_fail(cudaGetLastError(), "kernel_rows_kernel<double>");
@@ -281,21 +301,21 @@ int launch_reduce_g(const float* gp, long long nctas, int width, float scale, fl
     note_launch();
     return cuda_fail(cudaGetLastError(), "reduce_g_kernel");
 }
-int launch_mvm_f64(const double* Z1, long long m, const double* Z2, long long n, long long ld, int J, int K,
+int launch_mvm_f64(const double* Z1, long long m, const double* Z2, long long n, long long ld, int J, int K, int base,
                    const double* c, const double* V, int t, double* out, cudaStream_t st) {
     if (m == 0) return OK;
     for (int t0 = 0; t0 < t; t0 += F64_TMAX) {
         const int tc = (t - t0 < F64_TMAX) ? (t - t0) : F64_TMAX;
-        mvm_fwd_f64_kernel<<<(unsigned)((m + 63) / 64), 64, 0, st>>>(Z1, m, Z2, n, ld, J, K, c, V, t, t0, tc, out);
+        mvm_fwd_f64_kernel<<<(unsigned)((m + 63) / 64), 64, 0, st>>>(Z1, m, Z2, n, ld, J, K, base, c, V, t, t0, tc, out);
     }
     note_launch();
     return cuda_fail(cudaGetLastError(), "mvm_fwd_f64_kernel");
 }
-int launch_quad_f64(const double* Z1, long long m, const double* Z2, long long n, long long ld, int J, int K,
+int launch_quad_f64(const double* Z1, long long m, const double* Z2, long long n, long long ld, int J, int K, int base,
                     const double* c, const double* L, const double* R, int t, double* dZ1, double* g, cudaStream_t st) {
     if (m == 0) return OK;
     const long long total = m * J;
-    quad_bwd_f64_kernel<<<(unsigned)((total + 63) / 64), 64, 0, st>>>(Z1, m, Z2, n, ld, J, K, c, L, R, t, dZ1, g);
+    quad_bwd_f64_kernel<<<(unsigned)((total + 63) / 64), 64, 0, st>>>(Z1, m, Z2, n, ld, J, K, base, c, L, R, t, dZ1, g);
     note_launch();
     return cuda_fail(cudaGetLastError(), "quad_bwd_f64_kernel");
 }

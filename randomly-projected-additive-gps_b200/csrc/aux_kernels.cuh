@@ -6,21 +6,22 @@ namespace rpgp {
 
 struct Layout {  // binary-compatible with rpgp_layout in include/rpgp.h
     int J, K, CP, nchunks, KP, G;
+    int base;   // base kernel of every group: 0 RBF, 1 Matern-1.5, 2 inverse multiquadric (kv_kernels.cuh)
 };
 
 int launch_pack_coords(const float* Z, long long n, long long ld, const Layout& lay, float scale, float* Zp, cudaStream_t st);
 int launch_pack_log2c(const float* c, const Layout& lay, float* nlc, cudaStream_t st);
 int launch_project(const float* X, long long n, int d, long long ldx, const float* W, const float* pre_inv,
                    const float* post_inv, const Layout& lay, float scale, float* Zp, cudaStream_t st);
-int launch_rows_f32(const float* Zr, long long P, const float* Z2, long long n, long long ld, int J, int K,
+int launch_rows_f32(const float* Zr, long long P, const float* Z2, long long n, long long ld, int J, int K, int base,
                     const float* c, float* out, long long ldo, cudaStream_t st);
-int launch_rows_f64(const double* Zr, long long P, const double* Z2, long long n, long long ld, int J, int K,
+int launch_rows_f64(const double* Zr, long long P, const double* Z2, long long n, long long ld, int J, int K, int base,
                     const double* c, double* out, long long ldo, cudaStream_t st);
 int launch_reduce_dz(const float* dzp, int nsplits, long long plane, float scale, float* dz, cudaStream_t st);
 int launch_reduce_g(const float* gp, long long nctas, int width, float scale, float* g, cudaStream_t st);
-int launch_mvm_f64(const double* Z1, long long m, const double* Z2, long long n, long long ld, int J, int K,
+int launch_mvm_f64(const double* Z1, long long m, const double* Z2, long long n, long long ld, int J, int K, int base,
                    const double* c, const double* V, int t, double* out, cudaStream_t st);
-int launch_quad_f64(const double* Z1, long long m, const double* Z2, long long n, long long ld, int J, int K,
+int launch_quad_f64(const double* Z1, long long m, const double* Z2, long long n, long long ld, int J, int K, int base,
                     const double* c, const double* L, const double* R, int t, double* dZ1, double* g, cudaStream_t st);
 int launch_axpy_rows(float alpha, const float* V, int ldv, long long m, int t, float* out, int ldo, cudaStream_t st);
 int launch_reduce_partials(const float* partial, int nparts, long long m, int TP, int t, float* out, int ldo, cudaStream_t st);

@@ -1,7 +1,9 @@
-// bwd_kn.cu -- instantiations of the quadratic-form row-gradient kernel, K > 1.
+// bwd_kn.cu -- instantiations of the quadratic-form row-gradient kernel, K > 1, RBF base kernel.
 #include "dispatch.cuh"
 namespace rpgp {
-int launch_grad_kn(int KP, int G, int CP, int TP, const GradArgs& a, dim3 grid, cudaStream_t st) {
+int launch_grad_kn_base(int KP, int G, int CP, int TP, int base, const GradArgs& a, dim3 grid, cudaStream_t st);   // bwd_kn_base.cu
+int launch_grad_kn(int KP, int G, int CP, int TP, int base, const GradArgs& a, dim3 grid, cudaStream_t st) {
+    if (base != BASE_RBF) return launch_grad_kn_base(KP, G, CP, TP, base, a, grid, st);
 #define RPGP_CASE(KPv, Gv, CPv, TPv) \
     if (KP == KPv && G == Gv && CP == CPv && TP == TPv) return run_grad<CPv, TPv, KPv, Gv>(a, grid, st);
     RPGP_KN_SHAPE_LIST(RPGP_CASE, 4)

@@ -24,9 +24,9 @@ inline int default_poly_pairs(int CP, int TP) {
     if (TP > 16) return 0;
     return CP >= 28 ? 3 : (CP >= 16 ? 2 : (CP >= 8 ? 1 : 0));
 }
-int launch_fwd_kn(int KP, int G, int CP, int TP, const MvmArgs& a, dim3 grid, cudaStream_t st);
+int launch_fwd_kn(int KP, int G, int CP, int TP, int base, const MvmArgs& a, dim3 grid, cudaStream_t st);
 int launch_grad_k1(int CP, int TP, const GradArgs& a, dim3 grid, cudaStream_t st);
-int launch_grad_kn(int KP, int G, int CP, int TP, const GradArgs& a, dim3 grid, cudaStream_t st);
+int launch_grad_kn(int KP, int G, int CP, int TP, int base, const GradArgs& a, dim3 grid, cudaStream_t st);
 
 #ifdef __CUDACC__
 template <typename KernelT>
@@ -38,9 +38,9 @@ inline int set_smem(KernelT kernel, size_t bytes) {
     return OK;
 }
 
-template <int CP, int TP, int KP, int G, int NP2 = 0>
+template <int CP, int TP, int KP, int G, int NP2 = 0, int BASE = 0>
 inline int run_fwd(const MvmArgs& a, dim3 grid, cudaStream_t st) {
-    auto kernel = mvm_fwd_kernel<CP, TP, KP, G, NP2>;
+    auto kernel = mvm_fwd_kernel<CP, TP, KP, G, NP2, BASE>;
     constexpr size_t smem = fwd_smem_bytes<CP, TP>();
     if (int rc = set_smem(kernel, smem)) return rc;
     kernel<<<grid, ROWS_PER_CTA, smem, st>>>(a);
@@ -48,15 +48,15 @@ inline int run_fwd(const MvmArgs& a, dim3 grid, cudaStream_t st) {
     return cuda_fail(cudaGetLastError(), "mvm_fwd_kernel launch");
 }
 
-template <int CP, int TP, int KP, int G>
+template <int CP, int TP, int KP, int G, int BASE = 0>
 inline int run_grad(const GradArgs& a, dim3 grid, cudaStream_t st) {
     if (a.symmetric) {
-        auto kernel = quad_rowgrad_kernel<CP, TP, KP, G, true>;
+        auto kernel = quad_rowgrad_kernel<CP, TP, KP, G, true, BASE>;
         constexpr size_t smem = grad_smem_bytes<CP, TP>(true);
         if (int rc = set_smem(kernel, smem)) return rc;
         kernel<<<grid, ROWS_PER_CTA, smem, st>>>(a);
     } else {
-        auto kernel = quad_rowgrad_kernel<CP, TP, KP, G, false>;
+        auto kernel = quad_rowgrad_kernel<CP, TP, KP, G, false, BASE>;
         constexpr size_t smem = grad_smem_bytes<CP, TP>(false);
         if (int rc = set_smem(kernel, smem)) return rc;
         kernel<<<grid, ROWS_PER_CTA, smem, st>>>(a);

@@ -71,7 +71,44 @@ struct RowCoords {
     f32x2 z[CP / 2];                      // packed row coordinates
     f32x2 c2[(KP == 1) ? CP / 2 : 1];     // K=1: packed -log2c per projection pair
     float cg[(KP == 1) ? 1 : G];          // K>1: -log2c per group
+    float cw[(KP == 1) ? 1 : G];          // K>1, non-RBF base kernels: c per group (the weight multiplies outside the base function)
 };
+
+// ---- base kernels (training_routines.py:57-83, imq_kernel.py:8-9,47) ---------------------------------------------
+// u = scaled squared distance of a group (natural d^2 = 2 ln2 * u).  value: k = c f(d^2); slope: kz = -(dk/du) / ln2, the factor the
+// row-gradient kernel multiplies the coordinate differences with (its reducer applies -2 ln2, which is exact for the RBF k = 2^-u).
+constexpr int BASE_RBF = 0, BASE_MATERN15 = 1, BASE_IMQ = 2;
+constexpr float MATERN_C = 4.1588830833596715f;      // 3 * 2 ln2: (sqrt3 r)^2 = MATERN_C * u
+constexpr float TWO_LN2_F = 1.3862943611198906f;
+
+template <int BASE>
+__device__ __forceinline__ float base_value(float u, float nl, float cw) {
+    if constexpr (BASE == BASE_RBF) {
+        return ex2_ftz(-(u + nl));
+    } else if constexpr (BASE == BASE_MATERN15) {
+        const float q = sqrtf(fmaxf(MATERN_C * u, 0.f));
+        return cw * fmaf(q, ex2_ftz(-q * LOG2E_F), ex2_ftz(-q * LOG2E_F));
+    } else {
+        return cw * rsqrtf(fmaf(TWO_LN2_F, u, 1.f));
+    }
+}
+
+template <int BASE>
+__device__ __forceinline__ void base_value_slope(float u, float nl, float cw, float& k, float& kz) {
+    if constexpr (BASE == BASE_RBF) {
+        k = ex2_ftz(-(u + nl));
+        kz = k;
+    } else if constexpr (BASE == BASE_MATERN15) {
+        const float q = sqrtf(fmaxf(MATERN_C * u, 0.f));
+        const float e = cw * ex2_ftz(-q * LOG2E_F);
+        k = fmaf(q, e, e);
+        kz = 3.f * e;                      // -dk/du = c (MATERN_C / 2) e^-q ; / ln2 = 3 c e^-q
+    } else {
+        const float rs = rsqrtf(fmaf(TWO_LN2_F, u, 1.f));
+        k = cw * rs;
+        kz = k * rs * rs;                  // -dk/du = c ln2 rs^3
+    }
+}
 
 // 2^(-u) for a packed pair on the FMA + ALU pipes instead of the XU pipe (takes load off MUFU, the binding unit):
 // Cody-Waite split with the 1.5*2^23 magic constant (round-to-nearest integer n, |f| <= 1/2), degree-5 minimax polynomial
@@ -106,8 +143,9 @@ __device__ __forceinline__ f32x2 exp2_neg_poly2(f32x2 u) {
 }
 
 // NP2 = number of packed projection pairs per (i,i') whose exponential is evaluated by exp2_neg_poly2 (K = 1 only)
-template <int CP, int KP, int G, int NP2 = 0>
+template <int CP, int KP, int G, int NP2 = 0, int BASE = 0>
 __device__ __forceinline__ float pair_kernel_value(const RowCoords<CP, KP, G>& r, const float* __restrict__ zcol) {
+    static_assert(BASE == 0 || KP > 1, "non-RBF base kernels use the group layouts (K = 1 is stored with KP = 2)");
     // zcol: CP floats of one column in shared memory (16 B aligned)
     f32x2 zj[CP / 2];
 #pragma unroll
@@ -142,7 +180,7 @@ __device__ __forceinline__ float pair_kernel_value(const RowCoords<CP, KP, G>& r
         float s = 0.f;
 #pragma unroll
         for (int g = 0; g < G; ++g) {
-            f32x2 sq = pack2(r.cg[g], 0.f);
+            f32x2 sq = pack2(BASE == 0 ? r.cg[g] : 0.f, 0.f);
 #pragma unroll
             for (int p = 0; p < KP / 2; ++p) {
                 const f32x2 d = sub2(r.z[g * (KP / 2) + p], zj[g * (KP / 2) + p]);
@@ -150,7 +188,8 @@ __device__ __forceinline__ float pair_kernel_value(const RowCoords<CP, KP, G>& r
             }
             float lo, hi;
             unpack2(sq, lo, hi);
-            s += ex2_ftz(-(lo + hi));
+            if constexpr (BASE == 0) s += ex2_ftz(-(lo + hi));
+            else s += base_value<BASE>(lo + hi, 0.f, r.cw[g]);
         }
         return s;
     }
@@ -169,7 +208,10 @@ __device__ __forceinline__ void load_row_coords(RowCoords<CP, KP, G>& r, const f
         for (int q = 0; q < CP / 2; ++q) r.c2[q] = pack2(__ldg(nlc + 2 * q), __ldg(nlc + 2 * q + 1));
     } else {
 #pragma unroll
-        for (int g = 0; g < G; ++g) r.cg[g] = __ldg(nlc + g);
+        for (int g = 0; g < G; ++g) {
+            r.cg[g] = __ldg(nlc + g);
+            r.cw[g] = ex2_ftz(-r.cg[g]);        // c = 2^-(-log2 c); 0 for padding groups (+inf)
+        }
     }
 }
 
@@ -179,7 +221,7 @@ __device__ __forceinline__ void load_row_coords(RowCoords<CP, KP, G>& r, const f
 template <int CP, int TP>
 constexpr size_t fwd_smem_bytes() { return 128 + (size_t)NSTAGE * TN * (CP + TP) * sizeof(float); }
 
-template <int CP, int TP, int KP, int G, int NP2 = 0>
+template <int CP, int TP, int KP, int G, int NP2 = 0, int BASE = 0>
 __global__ void __launch_bounds__(ROWS_PER_CTA, 2) mvm_fwd_kernel(const MvmArgs a) {
     static_assert(CP % 4 == 0 && TP % 4 == 0, "packed layouts (16 B rows for the bulk copies)");
     static_assert(KP == 1 || (KP % 2 == 0 && G * KP <= CP), "group layout");
@@ -236,7 +278,7 @@ __global__ void __launch_bounds__(ROWS_PER_CTA, 2) mvm_fwd_kernel(const MvmArgs 
         for (int q = 0; q < TP / 2; ++q) lo[q] = 0ull;
 #pragma unroll 2
         for (int c = 0; c < cols; ++c) {
-            const float sv = pair_kernel_value<CP, KP, G, NP2>(r, zt + c * CP);
+            const float sv = pair_kernel_value<CP, KP, G, NP2, BASE>(r, zt + c * CP);
             const f32x2 ss = pack2(sv, sv);
 #pragma unroll
             for (int q = 0; q < TP / 4; ++q) {
@@ -284,7 +326,7 @@ constexpr size_t grad_smem_bytes(bool symmetric) {
     return 128 + (size_t)NSTAGE * TN * (CP + (symmetric ? 2 : 1) * TP) * sizeof(float) + 8 * 32 * sizeof(float);
 }
 
-template <int CP, int TP, int KP, int G, bool SYM>
+template <int CP, int TP, int KP, int G, bool SYM, int BASE = 0>
 __global__ void __launch_bounds__(ROWS_PER_CTA, 1) quad_rowgrad_kernel(const GradArgs a) {
     extern __shared__ __align__(128) unsigned char smem_raw[];
     uint64_t* full = reinterpret_cast<uint64_t*>(smem_raw);
@@ -398,16 +440,17 @@ __global__ void __launch_bounds__(ROWS_PER_CTA, 1) quad_rowgrad_kernel(const Gra
 #pragma unroll
                 for (int g = 0; g < G; ++g) {
                     f32x2 d[KP / 2];
-                    f32x2 sq = pack2(r.cg[g], 0.f);
+                    f32x2 sq = pack2(BASE == 0 ? r.cg[g] : 0.f, 0.f);
 #pragma unroll
                     for (int p = 0; p < KP / 2; ++p) {
                         d[p] = sub2(r.z[g * (KP / 2) + p], zj[g * (KP / 2) + p]);
                         sq = fma2(d[p], d[p], sq);
                     }
-                    float lo, hi;
+                    float lo, hi, kv, kz;
                     unpack2(sq, lo, hi);
-                    const float w = ex2_ftz(-(lo + hi)) * S;
-                    gcg[g] += w;
+                    base_value_slope<BASE>(lo + hi, 0.f, r.cw[g], kv, kz);
+                    gcg[g] += kv * S;
+                    const float w = kz * S;
                     const f32x2 ww = pack2(w, w);
 #pragma unroll
                     for (int p = 0; p < KP / 2; ++p) gz[g * (KP / 2) + p] = fma2(ww, d[p], gz[g * (KP / 2) + p]);

@@ -18,7 +18,7 @@ LN2 = 0.6931471805599453
 
 class Layout(Structure):
     """mirror of rpgp_layout (include/rpgp.h)"""
-    _fields_ = [("J", c_int), ("K", c_int), ("CP", c_int), ("nchunks", c_int), ("KP", c_int), ("G", c_int)]
+    _fields_ = [("J", c_int), ("K", c_int), ("CP", c_int), ("nchunks", c_int), ("KP", c_int), ("G", c_int), ("base", c_int)]
 
     def key(self):
         return (self.J, self.K, self.CP, self.nchunks, self.KP, self.G)
@@ -33,6 +33,7 @@ SIGNATURES = {
     "rpgp_last_error": (c_char_p, []),
     "rpgp_launch_count": (ctypes.c_ulonglong, []),
     "rpgp_plan_layout": (c_int, [c_int, c_int, POINTER(Layout)]),
+    "rpgp_plan_layout_base": (c_int, [c_int, c_int, c_int, POINTER(Layout)]),
     "rpgp_padded_rhs": (c_int, [POINTER(Layout), c_int, c_int]),
     "rpgp_max_rhs": (c_int, [POINTER(Layout), c_int]),
     "rpgp_coord_scale": (c_double, []),
@@ -59,6 +60,14 @@ SIGNATURES = {
                                      c_int64, c_void_p]),
     "rpgp_mvm_fwd_f64": (c_int, [c_void_p, c_int64, c_void_p, c_int64, c_int64, c_int, c_int, c_void_p, c_void_p,
                                  c_int, c_void_p, c_void_p]),
+    "rpgp_kernel_rows_base_f32": (c_int, [c_void_p, c_int64, c_void_p, c_int64, c_int64, c_int, c_int, c_int, c_void_p, c_void_p,
+                                          c_int64, c_void_p]),
+    "rpgp_kernel_rows_base_f64": (c_int, [c_void_p, c_int64, c_void_p, c_int64, c_int64, c_int, c_int, c_int, c_void_p, c_void_p,
+                                          c_int64, c_void_p]),
+    "rpgp_mvm_fwd_base_f64": (c_int, [c_void_p, c_int64, c_void_p, c_int64, c_int64, c_int, c_int, c_int, c_void_p, c_void_p,
+                                      c_int, c_void_p, c_void_p]),
+    "rpgp_quad_bwd_base_f64": (c_int, [c_void_p, c_int64, c_void_p, c_int64, c_int64, c_int, c_int, c_int, c_void_p, c_void_p,
+                                       c_void_p, c_int, c_void_p, c_void_p, c_void_p]),
     "rpgp_quad_bwd_f64": (c_int, [c_void_p, c_int64, c_void_p, c_int64, c_int64, c_int, c_int, c_void_p, c_void_p,
                                   c_void_p, c_int, c_void_p, c_void_p, c_void_p]),
     "rpgp_kmv_host_f32": (c_int, [c_void_p, c_int64, c_void_p, c_int64, c_int, c_void_p, c_int, c_int, c_void_p,
@@ -112,12 +121,15 @@ def _stream(device=None):
 _layout_cache = {}
 
 
-def plan_layout(J, K):
-    key = (int(J), int(K))
+BASE_RBF, BASE_MATERN15, BASE_INVERSE_MQ = 0, 1, 2      # rpgp_base_kernel (include/rpgp.h)
+
+
+def plan_layout(J, K, base=BASE_RBF):
+    key = (int(J), int(K), int(base))
     lay = _layout_cache.get(key)
     if lay is None:
         lay = Layout()
-        _check(load().rpgp_plan_layout(key[0], key[1], ctypes.byref(lay)), "rpgp_plan_layout")
+        _check(load().rpgp_plan_layout_base(key[0], key[1], key[2], ctypes.byref(lay)), "rpgp_plan_layout_base")
         _layout_cache[key] = lay
     return lay
 
@@ -329,7 +341,7 @@ def quad_bwd(z1p, z2p, lay, nlc, L, R, symmetric, row_range=None, L_full=None, R
     return dz, g
 
 
-def kernel_rows(Zr, Z2, c, J, K):
+def kernel_rows(Zr, Z2, c, J, K, base=BASE_RBF):
     """dense K(Zr, Z2) (P x n) on natural coordinates, float32 or float64."""
     require_cuda(Zr, Z2, c)
     assert Zr.dtype == Z2.dtype and Zr.dtype in (torch.float32, torch.float64)
@@ -338,25 +350,25 @@ def kernel_rows(Zr, Z2, c, J, K):
     c = c.to(Zr.dtype).contiguous()
     P, n = Zr.shape[0], Z2.shape[0]
     out = torch.empty((P, n), dtype=Zr.dtype, device=Zr.device)
-    fn = load().rpgp_kernel_rows_f32 if Zr.dtype == torch.float32 else load().rpgp_kernel_rows_f64
+    fn = load().rpgp_kernel_rows_base_f32 if Zr.dtype == torch.float32 else load().rpgp_kernel_rows_base_f64
     with torch.cuda.device(Zr.device):
-        _check(fn(_ptr(Zr), P, _ptr(Z2), n, J * K, J, K, _ptr(c), _ptr(out), n, _stream(Zr.device)), "rpgp_kernel_rows")
+        _check(fn(_ptr(Zr), P, _ptr(Z2), n, J * K, J, K, int(base), _ptr(c), _ptr(out), n, _stream(Zr.device)), "rpgp_kernel_rows")
     return out
 
 
-def mvm_fwd_f64(Z1, Z2, c, J, K, V):
+def mvm_fwd_f64(Z1, Z2, c, J, K, V, base=BASE_RBF):
     require_cuda(Z1, Z2, c, V)
     Z1, Z2, V = Z1.contiguous(), Z2.contiguous(), V.contiguous()
     c = c.to(torch.float64).contiguous()
     m, n, t = Z1.shape[0], Z2.shape[0], V.shape[1]
     out = torch.empty((m, t), dtype=torch.float64, device=V.device)
     with torch.cuda.device(V.device):
-        _check(load().rpgp_mvm_fwd_f64(_ptr(Z1), m, _ptr(Z2), n, J * K, J, K, _ptr(c), _ptr(V), t, _ptr(out),
-                                       _stream(V.device)), "rpgp_mvm_fwd_f64")
+        _check(load().rpgp_mvm_fwd_base_f64(_ptr(Z1), m, _ptr(Z2), n, J * K, J, K, int(base), _ptr(c), _ptr(V), t, _ptr(out),
+                                            _stream(V.device)), "rpgp_mvm_fwd_f64")
     return out
 
 
-def quad_bwd_f64(Z1, Z2, c, J, K, L, R):
+def quad_bwd_f64(Z1, Z2, c, J, K, L, R, base=BASE_RBF):
     """(dG/dZ1, g = dG/d ln c) for the FP64 path."""
     require_cuda(Z1, Z2, c, L, R)
     Z1, Z2, L, R = Z1.contiguous(), Z2.contiguous(), L.contiguous(), R.contiguous()
@@ -365,8 +377,8 @@ def quad_bwd_f64(Z1, Z2, c, J, K, L, R):
     dZ1 = torch.zeros_like(Z1)
     g = torch.zeros((J,), dtype=torch.float64, device=Z1.device)
     with torch.cuda.device(Z1.device):
-        _check(load().rpgp_quad_bwd_f64(_ptr(Z1), m, _ptr(Z2), n, J * K, J, K, _ptr(c), _ptr(L), _ptr(R), t,
-                                        _ptr(dZ1), _ptr(g), _stream(Z1.device)), "rpgp_quad_bwd_f64")
+        _check(load().rpgp_quad_bwd_base_f64(_ptr(Z1), m, _ptr(Z2), n, J * K, J, K, int(base), _ptr(c), _ptr(L), _ptr(R), t,
+                                             _ptr(dZ1), _ptr(g), _stream(Z1.device)), "rpgp_quad_bwd_f64")
     return dZ1, g
 
 

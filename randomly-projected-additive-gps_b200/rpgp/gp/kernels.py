@@ -169,6 +169,32 @@ class RBFKernel(Kernel):
         return RPAdditiveLazyTensor(z1, z2, one, 1, D)
 
 
+class MaternKernel(RBFKernel):
+    """Matern nu = 1.5: (1 + sqrt3 d) exp(-sqrt3 d), d = |a/l - b/l| (gpytorch.kernels.MaternKernel as the reference selects it,
+    training_routines.py:64-70: nu=1.5 only).  Same operator, base kernel 1 of the fused kernels."""
+    _base = 1
+
+    def __init__(self, nu=1.5, **kwargs):
+        if nu != 1.5:
+            raise NotImplementedError("only nu=1.5 (what the reference's _map_to_kernel builds) is on the fused K.V path")
+        self.nu = nu
+        super().__init__(**kwargs)
+
+    def forward(self, x1, x2, diag=False, last_dim_is_batch=False, **params):
+        op = super().forward(x1, x2, diag=diag, last_dim_is_batch=last_dim_is_batch, **params)
+        op.base = self._base
+        return op
+
+
+class InverseMQKernel(MaternKernel):
+    """(d^2 + 1)^-1/2 on lengthscale-divided inputs (gp_models/kernels/imq_kernel.py:8-22,25-58; both the dense and the KeOps
+    class of the reference lower to this one operator)."""
+    _base = 2
+
+    def __init__(self, **kwargs):
+        RBFKernel.__init__(self, **kwargs)
+
+
 class ScaleKernel(Kernel):
     """outputscale * base_kernel"""
 
@@ -236,3 +262,12 @@ class AdditiveStructureKernel(Kernel):
         if not isinstance(res, RPAdditiveLazyTensor):
             raise NotImplementedError("AdditiveStructureKernel needs an RBF-based base kernel on the K.V hot path")
         return res
+
+
+class _KeOpsNamespace:
+    """gpytorch.kernels.keops.* as the reference selects it with keops=True (training_routines.py:60-70): one backend here"""
+    RBFKernel = RBFKernel
+    MaternKernel = MaternKernel
+
+
+keops = _KeOpsNamespace

@@ -74,6 +74,16 @@ class LazyTensor:
         return self.rows(torch.as_tensor(index, device=self.device))
 
 
+def base_function(base, sq):
+    """k(d^2) of the base kernels (include/rpgp.h rpgp_base_kernel), torch, elementwise"""
+    if base == 1:
+        q = (3.0 * sq).clamp_min(0).sqrt()
+        return (1.0 + q) * torch.exp(-q)
+    if base == 2:
+        return (sq + 1.0).rsqrt()
+    return torch.exp(-0.5 * sq)
+
+
 class RPAdditiveLazyTensor(LazyTensor):
     """K(Z1, Z2) = sum_j c_j exp(-1/2 |Z1[:, group j] - Z2[:, group j]|^2), never materialised.
 
@@ -82,7 +92,7 @@ class RPAdditiveLazyTensor(LazyTensor):
     `representation()` is (Z1[, Z2], c) and autograd chains the rest.
     """
 
-    def __init__(self, Z1, Z2, c, J, K):
+    def __init__(self, Z1, Z2, c, J, K, base=0):
         if Z1.dim() != 2:
             raise ValueError("RPAdditiveLazyTensor does not support batch mode (neither does GAMFunction)")
         if Z2 is not None and Z2.shape[-1] != Z1.shape[-1]:
@@ -95,6 +105,7 @@ class RPAdditiveLazyTensor(LazyTensor):
         if self.c.dim() == 0 or self.c.numel() == 1:
             self.c = self.c.reshape(1).expand(J)
         self.J, self.K = int(J), int(K)
+        self.base = int(base)       # base kernel of every group: 0 RBF, 1 Matern-1.5, 2 inverse multiquadric (include/rpgp.h)
         self._packed1 = self._packed2 = self._nlc = None
 
     # ---- structure ---------------------------------------------------------------------------------------------------
@@ -118,8 +129,8 @@ class RPAdditiveLazyTensor(LazyTensor):
 
     def _rebuild(self, *rep):
         if self.symmetric:
-            return RPAdditiveLazyTensor(rep[0], None, rep[1], self.J, self.K)
-        return RPAdditiveLazyTensor(rep[0], rep[1], rep[2], self.J, self.K)
+            return RPAdditiveLazyTensor(rep[0], None, rep[1], self.J, self.K, self.base)
+        return RPAdditiveLazyTensor(rep[0], rep[1], rep[2], self.J, self.K, self.base)
 
     def detach(self):
         return self._rebuild(*[r.detach() for r in self.representation()])
@@ -127,7 +138,7 @@ class RPAdditiveLazyTensor(LazyTensor):
     def _transpose_nonbatch(self):
         if self.symmetric:
             return self
-        return RPAdditiveLazyTensor(self.Z2, self.Z1, self.c, self.J, self.K)
+        return RPAdditiveLazyTensor(self.Z2, self.Z1, self.c, self.J, self.K, self.base)
 
     def transpose(self, a=-2, b=-1):
         return self._transpose_nonbatch()
@@ -136,7 +147,7 @@ class RPAdditiveLazyTensor(LazyTensor):
 
     def scale(self, s):
         """outputscale * K  (ScaleKernel)"""
-        return RPAdditiveLazyTensor(self.Z1, self.Z2, self.c * s, self.J, self.K)
+        return RPAdditiveLazyTensor(self.Z1, self.Z2, self.c * s, self.J, self.K, self.base)
 
     __mul__ = scale
     __rmul__ = scale
@@ -147,6 +158,8 @@ class RPAdditiveLazyTensor(LazyTensor):
         (AdditiveKernel / SumLazyTensor); narrower groups are zero-padded to the widest K."""
         ops_list = list(ops_list)
         first = ops_list[0]
+        if any(o.base != first.base for o in ops_list):
+            raise NotImplementedError("a sum of different base kernels does not lower to one fused operator")
         Kmax = max(o.K for o in ops_list)
         sym = all(o.symmetric for o in ops_list)
 
@@ -160,7 +173,7 @@ class RPAdditiveLazyTensor(LazyTensor):
         Z1 = torch.cat([widen(o.Z1, o) for o in ops_list], dim=-1)
         Z2 = None if sym else torch.cat([widen(o.Z1 if o.symmetric else o.Z2, o) for o in ops_list], dim=-1)
         c = torch.cat([o.c.reshape(-1) for o in ops_list])
-        return RPAdditiveLazyTensor(Z1, Z2, c, sum(o.J for o in ops_list), Kmax)
+        return RPAdditiveLazyTensor(Z1, Z2, c, sum(o.J for o in ops_list), Kmax, first.base)
 
     def __add__(self, other):
         if isinstance(other, RPAdditiveLazyTensor):
@@ -172,7 +185,7 @@ class RPAdditiveLazyTensor(LazyTensor):
         """Product of single-group RBF operators on disjoint coordinates = one RBF on the concatenated coordinates
         (ProductKernel of 1-D RBFs, polynomial_projection_kernels.py:88-92)."""
         ops_list = list(ops_list)
-        if any(o.J != 1 for o in ops_list):
+        if any(o.J != 1 or o.base != 0 for o in ops_list):
             raise NotImplementedError("only products of single-group RBF kernels lower to the fused operator")
         sym = all(o.symmetric for o in ops_list)
         Z1 = torch.cat([o.Z1 for o in ops_list], dim=-1)
@@ -187,8 +200,8 @@ class RPAdditiveLazyTensor(LazyTensor):
         if self.dtype != torch.float32:
             return
         if self._packed1 is None:
-            self._packed1 = ops.Packed(self.Z1, self.J, self.K)
-            self._packed2 = self._packed1 if self.symmetric else ops.Packed(self.Z2, self.J, self.K)
+            self._packed1 = ops.Packed(self.Z1, self.J, self.K, self.base)
+            self._packed2 = self._packed1 if self.symmetric else ops.Packed(self.Z2, self.J, self.K, self.base)
             self._nlc = ops.pack_weights(self.c, self._packed1.lay)
 
     # ---- arithmetic ------------------------------------------------------------------------------------------------------
@@ -199,18 +212,18 @@ class RPAdditiveLazyTensor(LazyTensor):
         with torch.no_grad():
             if self.symmetric and rdist.world_size() > 1:
                 out = ops.kmv_partitioned(self.Z1.detach(), self.c.detach(), self.J, self.K, V.detach(),
-                                          packed=self._packed1, nlc=self._nlc)
+                                          packed=self._packed1, nlc=self._nlc, base=self.base)
             else:
                 Z2 = self.Z1 if self.symmetric else self.Z2
                 out = ops.kmv_raw(self.Z1.detach(), Z2.detach(), self.c.detach(), self.J, self.K, V.detach(),
-                                  packed1=self._packed1, packed2=self._packed2, nlc=self._nlc)
+                                  packed1=self._packed1, packed2=self._packed2, nlc=self._nlc, base=self.base)
         out = out.to(rhs.dtype)
         return out.squeeze(-1) if squeeze else out
 
     def matmul(self, rhs):
         """differentiable product"""
         Z2 = self.Z1 if self.symmetric else self.Z2
-        return ops.kmatmul(self.Z1, Z2, self.c, self.J, self.K, rhs)
+        return ops.kmatmul(self.Z1, Z2, self.c, self.J, self.K, rhs, base=self.base)
 
     def _quad_form_derivative(self, left_vecs, right_vecs):
         """d/d(representation) of sum_col left[:,col]^T K right[:,col]  (no graph; used by the MLL backward)."""
@@ -223,14 +236,14 @@ class RPAdditiveLazyTensor(LazyTensor):
                 rr = None if part.world == 1 else (part.r0, part.r1)
                 dZ, _, dc = ops.quad_form_grads(self.Z1.detach(), self.Z1.detach(), self.c.detach(), self.J, self.K,
                                                 L.detach(), R.detach(), True, packed1=self._packed1, nlc=self._nlc,
-                                                row_range=rr)
+                                                row_range=rr, base=self.base)
                 if part.world > 1:
                     dZ = rdist.all_gather_rows(dZ.contiguous(), part)
                     dc = rdist.all_reduce_sum(dc.contiguous())
                 return dZ.to(self.Z1.dtype), dc.to(self.c.dtype)
             dZ1, dZ2, dc = ops.quad_form_grads(self.Z1.detach(), self.Z2.detach(), self.c.detach(), self.J, self.K,
                                                L.detach(), R.detach(), False, packed1=self._packed1,
-                                               packed2=self._packed2, nlc=self._nlc)
+                                               packed2=self._packed2, nlc=self._nlc, base=self.base)
             return dZ1.to(self.Z1.dtype), dZ2.to(self.Z2.dtype), dc.to(self.c.dtype)
 
     def diag(self):
@@ -239,7 +252,7 @@ class RPAdditiveLazyTensor(LazyTensor):
         if self.Z1.shape != self.Z2.shape:
             raise RuntimeError("diag of a non-square operator")
         d = (self.Z1 - self.Z2).reshape(self.Z1.shape[0], self.J, self.K)
-        return (self.c * torch.exp(-0.5 * (d * d).sum(-1))).sum(-1)
+        return (self.c * base_function(self.base, (d * d).sum(-1))).sum(-1)
 
     _approx_diag = diag
 
@@ -248,12 +261,12 @@ class RPAdditiveLazyTensor(LazyTensor):
         Z2 = self.Z1 if self.symmetric else self.Z2
         with torch.no_grad():
             return ops.kernel_rows_raw(self.Z1.detach()[index].contiguous(), Z2.detach().contiguous(), self.c.detach(),
-                                       self.J, self.K)
+                                       self.J, self.K, self.base)
 
     def evaluate(self):
         """dense matrix (small n only), differentiable"""
         Z2 = self.Z1 if self.symmetric else self.Z2
-        return ops.kdense(self.Z1, Z2, self.c, self.J, self.K)
+        return ops.kdense(self.Z1, Z2, self.c, self.J, self.K, self.base)
 
 
 class DenseLazyTensor(LazyTensor):

@@ -34,8 +34,8 @@ class Packed:
 
     __slots__ = ("zp", "lay", "n")
 
-    def __init__(self, Z, J, K):
-        self.lay = _lib.plan_layout(J, K)
+    def __init__(self, Z, J, K, base=0):
+        self.lay = _lib.plan_layout(J, K, base)
         self.zp = _lib.pack_coords(Z.detach().contiguous(), self.lay)
         self.n = Z.shape[0]
 
@@ -75,15 +75,15 @@ def _check_operands(Z1, Z2, J, K):
 # ----------------------------------------------------------------------------------------------------------------------
 # raw (non-differentiable) calls
 # ----------------------------------------------------------------------------------------------------------------------
-def kmv_raw(Z1, Z2, c, J, K, V, packed1=None, packed2=None, nlc=None, row_range=None):
+def kmv_raw(Z1, Z2, c, J, K, V, packed1=None, packed2=None, nlc=None, row_range=None, base=0):
     """K(Z1[rows], Z2) @ V without autograd.  `packed*` / `nlc` let the caller reuse the packed operands across the
     many products of one CG solve (Z^ is computed once per step)."""
     c = _expand_c(c, J, Z1)
     if Z1.dtype == torch.float64:
         z1 = Z1 if row_range is None else Z1[row_range[0]:row_range[1]]
-        return _lib.mvm_fwd_f64(z1, Z2, c, J, K, V.to(torch.float64))
-    p1 = packed1 or Packed(Z1, J, K)
-    p2 = packed2 or (p1 if Z2 is Z1 else Packed(Z2, J, K))
+        return _lib.mvm_fwd_f64(z1, Z2, c, J, K, V.to(torch.float64), base=base)
+    p1 = packed1 or Packed(Z1, J, K, base)
+    p2 = packed2 or (p1 if Z2 is Z1 else Packed(Z2, J, K, base))
     nlc = nlc if nlc is not None else pack_weights(c, p1.lay)
     V = V.contiguous().float()
     if _use_sym(p1, p2, V.shape[1], row_range):
@@ -91,7 +91,7 @@ def kmv_raw(Z1, Z2, c, J, K, V, packed1=None, packed2=None, nlc=None, row_range=
     return _lib.mvm_fwd(p1.zp, p2.zp, p1.lay, nlc, V, row_range=row_range)
 
 
-def quad_form_grads(Z1, Z2, c, J, K, L, R, symmetric, packed1=None, packed2=None, nlc=None, row_range=None):
+def quad_form_grads(Z1, Z2, c, J, K, L, R, symmetric, packed1=None, packed2=None, nlc=None, row_range=None, base=0):
     """Gradients of sum_col L[:,col]^T K(Z1,Z2) R[:,col].
 
     symmetric (Z2 is Z1): returns (dZ, None, dc) with dZ the TOTAL derivative (both roles), for rows `row_range`
@@ -104,27 +104,27 @@ def quad_form_grads(Z1, Z2, c, J, K, L, R, symmetric, packed1=None, packed2=None
         if symmetric:
             rr = row_range or (0, Z1.shape[0])
             z1 = Z1[rr[0]:rr[1]]
-            dA, g = _lib.quad_bwd_f64(z1, Z1, c, J, K, L[rr[0]:rr[1]], R)
-            dB, _ = _lib.quad_bwd_f64(z1, Z1, c, J, K, R[rr[0]:rr[1]], L)
+            dA, g = _lib.quad_bwd_f64(z1, Z1, c, J, K, L[rr[0]:rr[1]], R, base=base)
+            dB, _ = _lib.quad_bwd_f64(z1, Z1, c, J, K, R[rr[0]:rr[1]], L, base=base)
             return dA + dB, None, g / c
-        dZ1, g = _lib.quad_bwd_f64(Z1, Z2, c, J, K, L, R)
-        dZ2, _ = _lib.quad_bwd_f64(Z2, Z1, c, J, K, R, L)
+        dZ1, g = _lib.quad_bwd_f64(Z1, Z2, c, J, K, L, R, base=base)
+        dZ2, _ = _lib.quad_bwd_f64(Z2, Z1, c, J, K, R, L, base=base)
         return dZ1, dZ2, g / c
-    p1 = packed1 or Packed(Z1, J, K)
+    p1 = packed1 or Packed(Z1, J, K, base)
     lay = p1.lay
     nlc = nlc if nlc is not None else pack_weights(c, lay)
     L, R = L.contiguous().float(), R.contiguous().float()
     if symmetric:
         dzp, g = _lib.quad_bwd(p1.zp, p1.zp, lay, nlc, L, R, symmetric=True, row_range=row_range)
         return unpack_coord_grad(dzp, lay), None, g[:J] / c
-    p2 = packed2 or Packed(Z2, J, K)
+    p2 = packed2 or Packed(Z2, J, K, base)
     dzp1, g = _lib.quad_bwd(p1.zp, p2.zp, lay, nlc, L, R, symmetric=False)
     dzp2, _ = _lib.quad_bwd(p2.zp, p1.zp, lay, nlc, R, L, symmetric=False)
     return unpack_coord_grad(dzp1, lay), unpack_coord_grad(dzp2, lay), g[:J] / c
 
 
-def kernel_rows_raw(Zr, Z2, c, J, K):
-    return _lib.kernel_rows(Zr, Z2, _expand_c(c, J, Z2), J, K)
+def kernel_rows_raw(Zr, Z2, c, J, K, base=0):
+    return _lib.kernel_rows(Zr, Z2, _expand_c(c, J, Z2), J, K, base)
 
 
 # ----------------------------------------------------------------------------------------------------------------------
@@ -134,39 +134,39 @@ class _KMatmul(torch.autograd.Function):
     """out = K(Z1, Z2) @ V; backward = quadratic-form derivative with L = grad_out, R = V, and K^T @ grad_out."""
 
     @staticmethod
-    def forward(ctx, Z1, Z2, c, V, J, K, symmetric):
+    def forward(ctx, Z1, Z2, c, V, J, K, symmetric, base=0):
         _check_operands(Z1, Z2, J, K)
         c = _expand_c(c, J, Z1)
-        ctx.J, ctx.K, ctx.symmetric = J, K, symmetric
+        ctx.J, ctx.K, ctx.symmetric, ctx.base = J, K, symmetric, base
         ctx.save_for_backward(Z1, Z2, c, V)
         Vc = V.to(Z1.dtype)
-        return kmv_raw(Z1, Z1 if symmetric else Z2, c, J, K, Vc).to(V.dtype)
+        return kmv_raw(Z1, Z1 if symmetric else Z2, c, J, K, Vc, base=base).to(V.dtype)
 
     @staticmethod
     def backward(ctx, grad_out):
         Z1, Z2, c, V = ctx.saved_tensors
-        J, K, sym = ctx.J, ctx.K, ctx.symmetric
+        J, K, sym, base = ctx.J, ctx.K, ctx.symmetric, ctx.base
         gZ1 = gZ2 = gc = gV = None
         g = grad_out.contiguous()
         need_k = ctx.needs_input_grad[0] or ctx.needs_input_grad[1] or ctx.needs_input_grad[2]
         if need_k:
             if sym:
-                dZ, _, dc = quad_form_grads(Z1, Z1, c, J, K, g, V, symmetric=True)
+                dZ, _, dc = quad_form_grads(Z1, Z1, c, J, K, g, V, symmetric=True, base=base)
                 gZ1, gc = dZ.to(Z1.dtype), dc.to(c.dtype)
             else:
-                dZ1, dZ2, dc = quad_form_grads(Z1, Z2, c, J, K, g, V, symmetric=False)
+                dZ1, dZ2, dc = quad_form_grads(Z1, Z2, c, J, K, g, V, symmetric=False, base=base)
                 gZ1, gZ2, gc = dZ1.to(Z1.dtype), dZ2.to(Z2.dtype), dc.to(c.dtype)
         if ctx.needs_input_grad[3]:
-            gV = kmv_raw(Z1 if sym else Z2, Z1, c, J, K, g.to(Z1.dtype)).to(V.dtype)  # K^T g
-        return gZ1, gZ2, gc, gV, None, None, None
+            gV = kmv_raw(Z1 if sym else Z2, Z1, c, J, K, g.to(Z1.dtype), base=base).to(V.dtype)  # K^T g
+        return gZ1, gZ2, gc, gV, None, None, None, None
 
 
-def kmatmul(Z1, Z2, c, J, K, V):
+def kmatmul(Z1, Z2, c, J, K, V, base=0):
     """Differentiable K(Z1, Z2) @ V.  Pass the same tensor object for Z1 and Z2 to use the symmetric kernels."""
     squeeze = V.dim() == 1
     V2 = V.unsqueeze(-1) if squeeze else V
     sym = Z2 is Z1
-    out = _KMatmul.apply(Z1, Z1 if sym else Z2, torch.as_tensor(c, device=Z1.device), V2, J, K, sym)
+    out = _KMatmul.apply(Z1, Z1 if sym else Z2, torch.as_tensor(c, device=Z1.device), V2, J, K, sym, base)
     return out.squeeze(-1) if squeeze else out
 
 
@@ -175,17 +175,17 @@ class _KDense(torch.autograd.Function):
     with L = grad, R = identity, processed in column blocks."""
 
     @staticmethod
-    def forward(ctx, Z1, Z2, c, J, K, symmetric):
+    def forward(ctx, Z1, Z2, c, J, K, symmetric, base=0):
         _check_operands(Z1, Z2, J, K)
         c = _expand_c(c, J, Z1)
-        ctx.J, ctx.K, ctx.symmetric = J, K, symmetric
+        ctx.J, ctx.K, ctx.symmetric, ctx.base = J, K, symmetric, base
         ctx.save_for_backward(Z1, Z2, c)
-        return kernel_rows_raw(Z1.detach().contiguous(), (Z1 if symmetric else Z2).detach().contiguous(), c, J, K)
+        return kernel_rows_raw(Z1.detach().contiguous(), (Z1 if symmetric else Z2).detach().contiguous(), c, J, K, base)
 
     @staticmethod
     def backward(ctx, G):
         Z1, Z2, c = ctx.saved_tensors
-        J, K, sym = ctx.J, ctx.K, ctx.symmetric
+        J, K, sym, base = ctx.J, ctx.K, ctx.symmetric, ctx.base
         m, n = G.shape
         Zb = Z1 if sym else Z2
         dZ1 = torch.zeros_like(Z1)
@@ -197,30 +197,30 @@ class _KDense(torch.autograd.Function):
             c1 = min(n, c0 + blk)
             L = G[:, c0:c1].contiguous()
             R = eye[:, c0:c1].contiguous()
-            a, b, g = quad_form_grads(Z1, Zb, c, J, K, L, R, symmetric=False)
+            a, b, g = quad_form_grads(Z1, Zb, c, J, K, L, R, symmetric=False, base=base)
             dZ1 += a
             dZ2 += b
             dc += g
         if sym:
-            return dZ1 + dZ2, None, dc, None, None, None
-        return dZ1, dZ2, dc, None, None, None
+            return dZ1 + dZ2, None, dc, None, None, None, None
+        return dZ1, dZ2, dc, None, None, None, None
 
 
-def kdense(Z1, Z2, c, J, K):
+def kdense(Z1, Z2, c, J, K, base=0):
     sym = Z2 is Z1
-    return _KDense.apply(Z1, Z1 if sym else Z2, torch.as_tensor(c, device=Z1.device), J, K, sym)
+    return _KDense.apply(Z1, Z1 if sym else Z2, torch.as_tensor(c, device=Z1.device), J, K, sym, base)
 
 
 # ----------------------------------------------------------------------------------------------------------------------
 # row-partitioned products (multi-GPU): each rank computes its row block, NCCL all-gather rebuilds the product
 # ----------------------------------------------------------------------------------------------------------------------
-def kmv_partitioned(Z, c, J, K, V, packed=None, nlc=None):
+def kmv_partitioned(Z, c, J, K, V, packed=None, nlc=None, base=0):
     """Symmetric K(Z,Z) @ V with the rows of K split over the ranks of the default process group."""
     part = rdist.partition(Z.shape[0])
     if part.world == 1:
-        return kmv_raw(Z, Z, c, J, K, V, packed1=packed, packed2=packed, nlc=nlc)
+        return kmv_raw(Z, Z, c, J, K, V, packed1=packed, packed2=packed, nlc=nlc, base=base)
     if Z.dtype == torch.float32:
-        p = packed or Packed(Z, J, K)
+        p = packed or Packed(Z, J, K, base)
         if _use_sym(p, p, V.shape[1], None):
             # symmetric tensor-core kernel: rank r owns the unique block pairs of its share of the 128-row blocks and
             # produces partial sums for ALL rows -> the exchange is an all-reduce (sum) instead of an all-gather
@@ -230,5 +230,5 @@ def kmv_partitioned(Z, c, J, K, V, packed=None, nlc=None):
             w = nlc if nlc is not None else pack_weights(_expand_c(c, J, Z), p.lay)
             out = _lib.mvm_sym(p.zp, p.lay, w, V.contiguous().float(), block_range=(b0, b1))
             return rdist.all_reduce_sum(out)
-    blk = kmv_raw(Z, Z, c, J, K, V, packed1=packed, packed2=packed, nlc=nlc, row_range=(part.r0, part.r1))
+    blk = kmv_raw(Z, Z, c, J, K, V, packed1=packed, packed2=packed, nlc=nlc, row_range=(part.r0, part.r1), base=base)
     return rdist.all_gather_rows(blk, part)

@@ -25,7 +25,7 @@ from gp_models.kernels import (CustomAdditiveKernel, GeneralizedProjectionKernel
                                PolynomialProjectionKernel, ScaledProjectionKernel, StrictlyAdditiveKernel)
 from gp_models.models import ExactGPModel
 from rpgp import gp as gpytorch
-from rpgp.gp.kernels import RBFKernel, ScaleKernel
+from rpgp.gp.kernels import InverseMQKernel, MaternKernel, RBFKernel, ScaleKernel
 
 SPEC_DIR = os.path.join(os.path.dirname(os.path.abspath(__file__)), "model_specs")
 HOT_PATH_KINDS = ("rp_poly", "additive_rp", "strictly_additive", "additive", "general_rp_poly")
@@ -66,15 +66,21 @@ def _sample_from_range(num_samples, range_):
 
 
 def _map_to_kernel(return_object, kernel_type, keops, **key_words):
-    """Base-kernel lookup.  Only RBF is fused; `keops` is accepted and ignored: there is a single backend -- the
-    hand-written kernels replace both the dense and the KeOps route of the reference (:57-63)."""
+    """Base-kernel lookup (reference :52-83).  `keops` is accepted and ignored: there is a single backend -- the hand-written
+    kernels replace both the dense and the KeOps route of the reference.  RBF, Matern (nu = 1.5) and the inverse multiquadric run
+    in the fused kernels; the cosine kernel is not a function of the squared distance the operator is built on (and has no KeOps
+    form in the reference either)."""
     if return_object:
         cls, kwargs = _map_to_kernel(False, kernel_type, keops)
         return cls(**key_words, **kwargs)
     if kernel_type == "RBF":
         return RBFKernel, dict(**key_words)
-    if kernel_type in ("Matern", "InverseMQ", "Cosine"):
-        raise NotImplementedError("kernel_type %s is a 'next' row (SURVEY.md §8f-4); the fused K.V path is RBF" % kernel_type)
+    if kernel_type == "Matern":
+        return MaternKernel, dict(nu=1.5, **key_words)
+    if kernel_type == "InverseMQ":
+        return InverseMQKernel, dict(**key_words)
+    if kernel_type == "Cosine":
+        raise NotImplementedError("the cosine base kernel is outside the fused K.V path (DESIGN.md §9)")
     raise ValueError("Unknown kernel type")
 
 

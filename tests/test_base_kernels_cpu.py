@@ -1,0 +1,62 @@
+"""CPU tests of the base-kernel plumbing: oracle functions and their slopes, the torch restatement used for
+diagonals, the kernel-type lookup of training_routines, and the rules for combining operators."""
+import numpy as np
+import pytest
+import torch
+
+import training_routines as tr
+from gp_models.kernels import InverseMQKernel as MirrorIMQ, KeOpsInverseMQKernel, postprocess_inverse_mq
+from oracle import rpgp_oracle as orc
+from rpgp import lazy
+from rpgp.gp import kernels as gk
+
+
+@pytest.mark.parametrize("base", [0, 1, 2])
+def test_oracle_base_functions_and_slopes(base):
+    sq = np.linspace(0.0, 30.0, 301)[1:]
+    h = 1e-6
+    fd = (orc.base_f(base, sq + h) - orc.base_f(base, sq - h)) / (2 * h)
+    np.testing.assert_allclose(orc.base_df(base, sq), fd, rtol=1e-6, atol=1e-10)
+    assert abs(orc.base_f(base, np.array([0.0]))[0] - 1.0) < 1e-15            # k(x, x) = 1 for all three
+    t = torch.from_numpy(sq)
+    np.testing.assert_allclose(lazy.base_function(base, t).numpy(), orc.base_f(base, sq), rtol=1e-12)
+
+
+def test_oracle_dense_kernel_known_values():
+    # one group, one coordinate, distance 2: RBF e^-2, Matern (1 + 2 sqrt3) e^(-2 sqrt3), IMQ 5^-1/2
+    Z1, Z2 = np.array([[0.0]]), np.array([[2.0]])
+    want = [np.exp(-2.0), (1 + 2 * np.sqrt(3)) * np.exp(-2 * np.sqrt(3)), 5 ** -0.5]
+    for base in range(3):
+        assert abs(orc.additive_rbf_dense(Z1, Z2, [1.0], 1, 1, base=base)[0, 0] - want[base]) < 1e-15
+    assert abs(float(postprocess_inverse_mq(torch.tensor(4.0))) - want[2]) < 1e-7      # imq_kernel.py:8-9
+
+
+def test_kernel_type_lookup_matches_the_reference_table():
+    assert tr._map_to_kernel(False, "RBF", False) == (gk.RBFKernel, {})
+    assert tr._map_to_kernel(False, "Matern", True) == (gk.MaternKernel, {"nu": 1.5})
+    assert tr._map_to_kernel(False, "InverseMQ", False) == (gk.InverseMQKernel, {})
+    assert MirrorIMQ is gk.InverseMQKernel and KeOpsInverseMQKernel is gk.InverseMQKernel
+    assert gk.keops.RBFKernel is gk.RBFKernel and gk.keops.MaternKernel is gk.MaternKernel
+    with pytest.raises(NotImplementedError):
+        tr._map_to_kernel(False, "Cosine", False)
+    with pytest.raises(ValueError):
+        tr._map_to_kernel(False, "Periodic", False)
+    k = tr._map_to_kernel(True, "Matern", False, active_dims=[0])
+    assert isinstance(k, gk.MaternKernel) and k.nu == 1.5 and tuple(k.raw_lengthscale.shape) == (1, 1)
+    with pytest.raises(NotImplementedError):
+        gk.MaternKernel(nu=2.5)
+
+
+def test_operators_of_different_base_kernels_do_not_merge():
+    Z = torch.zeros(4, 2)
+    a = lazy.RPAdditiveLazyTensor(Z, None, torch.ones(2), 2, 1, base=1)
+    b = lazy.RPAdditiveLazyTensor(Z, None, torch.ones(2), 2, 1, base=1)
+    s = a + b
+    assert s.base == 1 and s.J == 4 and s._transpose_nonbatch().base == 1 and s.scale(2.0).base == 1
+    with pytest.raises(NotImplementedError):
+        lazy.RPAdditiveLazyTensor.sum([a, lazy.RPAdditiveLazyTensor(Z, None, torch.ones(2), 2, 1, base=0)])
+    one = lazy.RPAdditiveLazyTensor(Z[:, :1], None, torch.ones(1), 1, 1, base=2)
+    with pytest.raises(NotImplementedError):          # a product of non-RBF kernels is not a kernel of the summed distance
+        lazy.RPAdditiveLazyTensor.product([one, one])
+    op = gk.InverseMQKernel().forward(Z, Z)
+    assert op.base == 2

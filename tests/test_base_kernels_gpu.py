@@ -1,0 +1,132 @@
+"""GPU parity of the Matern-1.5 and inverse-multiquadric base kernels (reference training_routines.py:57-83,
+gp_models/kernels/imq_kernel.py) through the fused forward / gradient kernels, the dense-row kernel and the FP64 path, against
+the numpy oracle; then through the reference-facing kernel classes."""
+import warnings
+
+import numpy as np
+import pytest
+import torch
+
+import training_routines as tr
+from gp_models.models import ExactGPModel
+from oracle import rpgp_oracle as orc
+from rpgp import gp as gpytorch
+from rpgp import lazy, ops
+from rpgp.gp import settings
+
+pytestmark = pytest.mark.gpu
+DEV = torch.device("cuda:0")
+
+
+def rel(a, b):
+    a, b = np.asarray(a, np.float64), np.asarray(b, np.float64)
+    return np.linalg.norm(a - b) / max(np.linalg.norm(b), 1e-300)
+
+
+def data(m, n, J, K, t, seed):
+    rng = np.random.RandomState(seed)
+    Z1 = (rng.randn(m, J * K) / np.sqrt(K)).astype(np.float32)
+    Z2 = (rng.randn(n, J * K) / np.sqrt(K)).astype(np.float32)
+    c = (rng.rand(J) + 0.1).astype(np.float32)
+    V = rng.randn(n, t).astype(np.float32)
+    return Z1, Z2, c, V
+
+
+@pytest.mark.parametrize("base", [1, 2])
+@pytest.mark.parametrize("m,n,J,K,t", [(300, 700, 20, 1, 11), (257, 513, 7, 3, 4), (400, 400, 1, 20, 16), (130, 900, 40, 1, 1),
+                                       (64, 2000, 20, 5, 11)])
+def test_forward_and_rows_match_oracle(base, m, n, J, K, t):
+    Z1, Z2, c, V = data(m, n, J, K, t, seed=m + n + J + base)
+    d = lambda a: torch.from_numpy(a).to(DEV)
+    got = ops.kmv_raw(d(Z1), d(Z2), d(c), J, K, d(V), base=base).cpu().numpy()
+    ref = orc.kmv(Z1, Z2, c, J, K, V, base=base)
+    assert rel(got, ref) < 1e-5, rel(got, ref)
+    rows = ops.kernel_rows_raw(d(Z1[:9]), d(Z2), d(c), J, K, base).cpu().numpy()
+    assert rel(rows, orc.additive_rbf_dense(Z1[:9], Z2, c, J, K, base=base)) < 2e-6
+    got64 = ops.kmv_raw(d(Z1).double(), d(Z2).double(), d(c).double(), J, K, d(V).double(), base=base).cpu().numpy()
+    assert rel(got64, ref) < 1e-10
+    rows64 = ops.kernel_rows_raw(d(Z1[:9]).double(), d(Z2).double(), d(c).double(), J, K, base).cpu().numpy()
+    assert rel(rows64, orc.additive_rbf_dense(Z1[:9], Z2, c, J, K, base=base)) < 1e-12
+
+
+@pytest.mark.parametrize("base", [1, 2])
+@pytest.mark.parametrize("n,J,K,t", [(500, 20, 1, 11), (300, 6, 4, 3), (260, 1, 20, 16)])
+def test_quadratic_form_gradients_match_oracle(base, n, J, K, t):
+    Z1, Z2, c, _ = data(n, n + 37, J, K, t, seed=n + J + 10 * base)
+    rng = np.random.RandomState(3)
+    L, R = rng.randn(n, t).astype(np.float32), rng.randn(n + 37, t).astype(np.float32)
+    d = lambda a: torch.from_numpy(a).to(DEV)
+    dZ1, dZ2, dc = ops.quad_form_grads(d(Z1), d(Z2), d(c), J, K, d(L), d(R), symmetric=False, base=base)
+    r1, r2, rc = orc.quad_form_grads(Z1, Z2, c, J, K, L, R, base=base)
+    assert rel(dZ1.cpu().numpy(), r1) < 1e-4 and rel(dZ2.cpu().numpy(), r2) < 1e-4 and rel(dc.cpu().numpy(), rc) < 1e-4
+    # symmetric operator: total derivative w.r.t. Z (both roles)
+    Ls, Rs = L, R[:n]
+    dZ, _, dcs = ops.quad_form_grads(d(Z1), d(Z1), d(c), J, K, d(Ls), d(Rs), symmetric=True, base=base)
+    a, b, rcs = orc.quad_form_grads(Z1, Z1, c, J, K, Ls, Rs, base=base)
+    assert rel(dZ.cpu().numpy(), a + b) < 1e-4 and rel(dcs.cpu().numpy(), rcs) < 1e-4
+    # FP64 path
+    dZ1d, dZ2d, dcd = ops.quad_form_grads(d(Z1).double(), d(Z2).double(), d(c).double(), J, K, d(L).double(), d(R).double(),
+                                          symmetric=False, base=base)
+    assert rel(dZ1d.cpu().numpy(), r1) < 1e-9 and rel(dZ2d.cpu().numpy(), r2) < 1e-9 and rel(dcd.cpu().numpy(), rc) < 1e-9
+
+
+@pytest.mark.parametrize("kernel_type,base", [("Matern", 1), ("InverseMQ", 2)])
+def test_kernel_classes_lower_to_the_fused_operator(kernel_type, base):
+    """create_additive_rp_kernel(kernel_type=...) (training_routines.py:131-189): the operator carries the base kernel, its dense
+    evaluation equals the closed form, and MLL + gradients in FP32 (fused kernels) agree with the FP64 path."""
+    torch.manual_seed(0)
+    n, dd, J = 400, 6, 8
+    X = torch.rand(n, dd) * 4 - 2
+    y = torch.sin(X).sum(-1)
+    y = (y - y.mean()) / y.std()
+    kern = tr.create_additive_rp_kernel(dd, J, kernel_type=kernel_type, prescale=True, batch_kernel=False)
+    model = ExactGPModel(X, y, gpytorch.likelihoods.GaussianLikelihood(), kern).to(DEV)
+    Xd, yd = X.to(DEV), y.to(DEV)
+    op = model.covar_module(Xd).evaluate_kernel()
+    assert isinstance(op, lazy.RPAdditiveLazyTensor) and op.base == base and op.J == J and op.K == 1
+    Z = op.Z1.detach().cpu().double().numpy()
+    cc = op.c.detach().cpu().double().numpy()
+    assert rel(op.evaluate().detach().cpu().numpy(), orc.additive_rbf_dense(Z, Z, cc, J, 1, base=base)) < 2e-6
+    assert rel(op.diag().detach().cpu().numpy(), np.full(n, cc.sum())) < 1e-6
+
+    def loss_and_grads(m, Xi, yi):
+        m.train()
+        mll = gpytorch.mlls.ExactMarginalLogLikelihood(m.likelihood, m)
+        for p in m.parameters():
+            p.grad = None
+        loss = -mll(m(Xi), yi)
+        loss.backward()
+        return float(loss), {k: p.grad.detach().cpu().double().numpy() for k, p in m.named_parameters() if p.grad is not None}
+
+    with settings.max_cholesky_size(100000), warnings.catch_warnings():
+        warnings.simplefilter("ignore")
+        l32, g32 = loss_and_grads(model, Xd, yd)
+        import copy
+        m64 = copy.deepcopy(model).to(DEV, torch.float64)
+        l64, g64 = loss_and_grads(m64, Xd.double(), yd.double())
+    assert abs(l32 - l64) < 1e-4 * abs(l64)
+    assert set(g32) == set(g64) and len(g32) >= 3
+    for k in g64:
+        assert rel(g32[k], g64[k]) < 2e-3, (k, rel(g32[k], g64[k]))
+
+
+def test_training_with_an_inverse_multiquadric_kernel_learns_an_additive_target():
+    X = torch.rand(900, 5, generator=torch.Generator().manual_seed(1)) * 4 - 2
+    y = torch.sin(X).sum(-1)
+    y = (y - y.mean()) / y.std()
+    Xt = torch.rand(200, 5, generator=torch.Generator().manual_seed(2)) * 4 - 2
+    yt = torch.sin(Xt).sum(-1)
+    yt = (yt - torch.sin(X).sum(-1).mean()) / torch.sin(X).sum(-1).std()
+    spec = tr.load_model_spec("additive_rp_J20_K1")
+    spec["model_kwargs"]["kernel_type"] = "InverseMQ"
+    spec["train_kwargs"].update(max_iter=30, check_conv=False)
+    torch.manual_seed(3)
+    np.random.seed(3)
+    with settings.cg_tolerance(0.01), settings.eval_cg_tolerance(1e-3), warnings.catch_warnings():
+        warnings.simplefilter("ignore")
+        metrics, pred, model = tr.train_exact_gp(X, y, Xt, yt, spec["kind"], spec["model_kwargs"], spec["train_kwargs"],
+                                                 devices=("cuda:0",), skip_random_restart=True)
+    assert model.covar_module(X.to(DEV)).evaluate_kernel().base == 2
+    rmse = float(((pred - yt) ** 2).mean().sqrt())
+    assert rmse < 0.5, rmse
+    assert np.isfinite(metrics["test_nll"]) and np.isfinite(metrics["prior_train_nmll"])
