@@ -1,0 +1,773 @@
+// EXPERIMENT (not built): sym_tcd.cu with one group per hand-off, 4-deep D0 buffers, two register sets (the next tcgen05.ld in flight
+// under the current exponentials) and setmaxnreg rebalancing 88/64/48.  Correct (tools/tcd_check.py acc) but SLOWER on B200: n=100k
+// J=20,K=5 70.8 ms (shipped 51.6), J=1,K=20 23.8 ms (11.0), J=8,K=6 25.7 ms (19.2) -- kept for the record, see DESIGN.md section 8.
+
+// sym_tcd.cu -- symmetric K(Z,Z).V for K > 1 coordinates per projection group with the squared distances on the tensor cores.
+//
+// For a group of K coordinates the exponent of the kernel value is
+//     U[i,i'] = -log2 c + |z_i|^2 + |z_i'|^2 - 2 z_i.z_i'          (coordinates pre-scaled so that k = 2^-U)
+// and sym_tc5.cu spends 2K+1 FP32 lane-operations per (pair, group) on it -- for K = 5 / 20 the FMA pipe and the broadcast loads
+// of the column coordinates bind long before the XU pipe does.  Here U is an inner product of augmented vectors, six coordinates
+// per k-step of eight:
+//     A_i  = [ -2 z_i[6s..6s+5] , |z_i[6s..]|^2 (- log2 c in step 0) , 1 ]        B_i' = [ z_i'[6s..6s+5] , 1 , |z_i'[6s..]|^2 ]
+// evaluated by tcgen05.mma kind::tf32 with the 3xTF32 split (Ah.Bh + Al.Bh + Ah.Bl, FP32 accumulation in TMEM): the arithmetic
+// warps only read U back (tcgen05.ld, lane = row), take the exponential and add up the groups.  Everything downstream of the
+// kernel value -- the split of S, S.V on the row side, S^T.V on the column side, the FP64 accumulators -- is sym_tc5.cu's scheme.
+//
+// Accuracy.  The cancellation in U costs an absolute error proportional to |z|^2.  What keeps it small (tools/tcd_check.py adv,
+// profiles/tcd_accuracy_r01.txt): coordinates are centred on their column means (differences do not change); the split is
+// round-to-nearest for both parts (a truncating split biases every U by ~3e-7 |z|^2); every k-step carries the partial norms of
+// ITS six coordinates, so that the running sum in TMEM is a partial squared distance -- small for exactly the pairs that matter;
+// pairs i == i' get their exact value U = -log2 c.  The pre-pass records max |z - mean|^2 over rows and groups and the kernel runs
+// only while that stays below a bound (rpgp::tcd_gate_bound); otherwise the direct-difference kernel of sym_tc5.cu takes the launch
+// -- both are launched, one of them returns at once.
+//
+// Operands: the pre-pass (tcd_build_images_kernel) writes, per 128-row block and per 32-column tile, the exact shared-memory bytes
+// of the A / B operands (K-major, SWIZZLE_128B, tf32 part and remainder planes; a 128-byte line holds 4 k-steps) so that one bulk
+// copy per tile delivers a ready operand.  A chunk holds GT groups of KS = ceil(K/6) k-steps (GT*KS <= 4*NL, NL <= 2).
+//
+// CTA (one per SM, 24 warps):
+//   * 16 arithmetic warps in two teams of eight that take the tiles in turn (team = tile parity = S buffer): one team's exponentials
+//     fill the XU pipe while the other waits for its exponents, loads them, or splits and stores its S tile;
+//   * 4 epilogue warps (TMEM lane quadrants) for the column side; lane 0 of one of them issues the bulk copies;
+//   * 4 warps whose lane 0 issues one stream of MMAs each (a UTCHMMA blocks its issuing warp ~100-150 clk,
+//     profiles/umma_microbench_r01.txt): S.V, S^T.V, and the distance MMAs of the first / second group of a batch.
+// TMEM: D1 (row side) 2 x 32 columns, D2 (column side) 2 x 32, D0 (exponents) 2 teams x 4 buffers x 32 (one group each).
+#include <algorithm>
+#include <cstdlib>
+#include <cstring>
+#include <type_traits>
+
+#include "aux_kernels.cuh"
+#include "sym_tc.cuh"
+#include "sym_tc_dev.cuh"
+
+namespace rpgp {
+
+namespace {
+
+using namespace tcdev;
+
+constexpr int D_F = 4;            // tiles accumulated in TMEM per row-side epoch
+constexpr int D_ZST = 3;          // B-image stages
+constexpr int D_AW = 16;          // arithmetic warps
+constexpr int D_NPART = 4;        // column quarters of a tile
+constexpr int D_FC = T5_N / D_NPART;   // right-hand-side columns folded per arithmetic thread
+constexpr int D_NDI = 2;          // distance-MMA issuing warps (one per group of a batch)
+constexpr int D_ISSUERS = 2 + D_NDI; // row side, column side, distances
+constexpr int D_THREADS = 32 * (D_AW + 4 + D_ISSUERS);
+#ifndef TCD_SLEEP_NS
+#define TCD_SLEEP_NS 64
+#endif
+// registers: the kernel is launched with 80 per thread (768 x 80 <= 64 K); the arithmetic warps (two register sets of exponents)
+// take what the helper warps hand back: 512 x 88 + 128 x 64 + 128 x 48 = 59 392
+constexpr int D_REGS_ARITH = 88, D_REGS_EPI = 64, D_REGS_ISSUE = 48;
+constexpr int D_SLEEP = TCD_SLEEP_NS;   // back-off of the helper warps' barrier polls (ns)
+constexpr size_t D_WS_HEADER = 16384;   // workspace header: gate word, then column sums (doubles) from byte 1024
+constexpr float D_PAD = 16384.f;  // exponent of padding rows / groups: 2^-16384 == 0
+
+// shared-memory map (bytes from a 1024-aligned base)
+constexpr uint32_t D_S = 0;                    // S operand: buffer b at b*32768: tf32 part [128 rows][128 B], remainder 16384 B later
+constexpr uint32_t D_BC = 65536;               // B operand of the column side: V of this row block, 4 blocks x 4096 B
+constexpr uint32_t D_BT = 81920;               // B operand of the row side: V of the tile's columns, 2 stages x 4096 B
+constexpr uint32_t D_EPI = 90112;              // column-side epilogue exchange: 2 x [4 quadrants][16 rows][16] floats
+constexpr uint32_t D_AIMG = 98304;             // A operand of the distance MMAs: NL line sets x [tf32 part | remainder] x [128 rows][128 B]
+__host__ __device__ constexpr uint32_t d_bimg(int NL) { return D_AIMG + (uint32_t)NL * 32768u; }   // B operand: 3 stages x NL x [hi|lo] x [32][128 B]
+__host__ __device__ constexpr uint32_t d_bar(int NL) { return d_bimg(NL) + (uint32_t)D_ZST * NL * 8192u; }
+__host__ __device__ constexpr uint32_t d_smem_bytes(int NL) { return d_bar(NL) + 512 + 1024; }
+
+// TMEM columns
+constexpr uint32_t D_TM_D1 = 0, D_TM_D2 = 64, D_TM_D0 = 128;      // 128 + 4 x 64 = 384 columns in use, 512 allocated
+
+// barrier indices
+constexpr int BD_ZFULL = 0;      // [3]  bulk copy of a B image -> distance issuers
+constexpr int BD_BFULL = 3;      // [2]  bulk copy -> row-side MMA issuer (B tile of V)
+constexpr int BD_SFULL = 5;      // [2]  the tile's team -> MMA issuers (count 8)
+constexpr int BD_TDONE = 7;      // [2]  tcgen05.commit of the three S issuers (count 3)
+constexpr int BD_EREAD = 9;      // [2]  epilogue warps have read D2 (count 4)
+constexpr int BD_D1EMPTY = 11;   // [2]  arithmetic warps have folded an epoch of D1 (count 16)
+constexpr int BD_BCFULL = 13;    // [1]  bulk copy of the column-side B operand
+constexpr int BD_AFULL = 14;     // [1]  bulk copy of the A image
+constexpr int BD_D0FULL = 16;    // [2 teams][4]  tcgen05.commit of a group's distance MMAs
+constexpr int BD_D0FREE = 24;    // [2 teams][4]  the team's warps have read the group's exponents (count 8)
+
+__device__ __forceinline__ void tmem5_ld4(uint32_t taddr, float* v) {
+    uint32_t r[4];
+    asm volatile("tcgen05.ld.sync.aligned.32x32b.x4.b32 {%0,%1,%2,%3}, [%4];" : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]) : "r"(taddr));
+    asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+#pragma unroll
+    for (int q = 0; q < 4; ++q) v[q] = __uint_as_float(r[q]);
+}
+
+// four loads in flight, one wait
+__device__ __forceinline__ void tmem5_ld8x4(uint32_t t0, uint32_t t1, uint32_t t2, uint32_t t3, float* v0, float* v1, float* v2, float* v3) {
+    uint32_t r[32];
+    const uint32_t ta[4] = {t0, t1, t2, t3};
+#pragma unroll
+    for (int k = 0; k < 4; ++k)
+        asm volatile("tcgen05.ld.sync.aligned.32x32b.x8.b32 {%0,%1,%2,%3,%4,%5,%6,%7}, [%8];"
+                     : "=r"(r[8 * k]), "=r"(r[8 * k + 1]), "=r"(r[8 * k + 2]), "=r"(r[8 * k + 3]), "=r"(r[8 * k + 4]), "=r"(r[8 * k + 5]),
+                       "=r"(r[8 * k + 6]), "=r"(r[8 * k + 7])
+                     : "r"(ta[k]));
+    asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+#pragma unroll
+    for (int q = 0; q < 8; ++q) {
+        v0[q] = __uint_as_float(r[q]); v1[q] = __uint_as_float(r[8 + q]); v2[q] = __uint_as_float(r[16 + q]); v3[q] = __uint_as_float(r[24 + q]);
+    }
+}
+
+__device__ __forceinline__ void mbar_wait_ns(int ns, uint64_t* bar, uint32_t parity) {
+    uint32_t done = 0;
+    while (true) {
+        asm volatile(
+            "{\n\t.reg .pred p;\n\t"
+            "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+            "selp.u32 %0, 1, 0, p;\n\t}\n"
+            : "=r"(done)
+            : "r"(smem_u32(bar)), "r"(parity)
+            : "memory");
+        if (done) break;
+        if (ns > 0) __nanosleep(ns);
+    }
+}
+
+__device__ __forceinline__ float tf32_rn(float x) {
+    uint32_t r;
+    asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(r) : "f"(x));
+    return __uint_as_float(r);
+}
+
+struct SymDArgs {
+    const unsigned char* aimg;   // [nchunks][nblocks][NL][2][128][128 B]
+    const unsigned char* bimg;   // [nchunks][nblocks*4][NL][2][32][128 B]
+    const float* bsplit;         // [nblocks*4][4096 B] pre-split right-hand sides
+    const float* nlc;            // [J] -log2 c per group
+    double* acc;                 // [n][16] FP64 accumulators
+    const unsigned* gate;        // pre-pass statistics of the centred squared group norms (sym_tc_dev.cuh: tcd_gate_open)
+    unsigned gate_max;
+    double gate_sum4_max;
+    long long n;
+    int nblocks, half, nsplits, rb_begin;
+    int G, KS, NB, GB, J;        // groups per chunk, k-steps per group, D0 batches per tile, groups per batch (<= 4), total groups
+    long long* dbg;              // RPGP_TCD_DBG: clock64 stamps of CTA (0,0,0), [64 tiles][8]
+    int sleep_ns;                // back-off of the helper warps' barrier polls
+    int diag;                    // diagnostics (RPGP_TCD_DIAG): 1 no column atomics, 2 no column MMAs, 4 no row MMAs, 8 no distance MMAs, 32 no D2 reads
+};
+
+}  // namespace
+
+#define TCD_STAMP(j, k) do { if (a.dbg && (j) < 64 && blockIdx.x == 7 && blockIdx.y == 0 && blockIdx.z == 0) a.dbg[(j) * 12 + (k)] = clock64(); } while (0)
+
+template <int NL>
+__global__ void __maxnreg__(80) mvm_sym_tcd_kernel(const SymDArgs a) {
+    if (!tcd_gate_open(a.gate, a.gate_max, a.gate_sum4_max)) return;   // coordinates too large for the cancellation in U: sym_tc5.cu's kernel takes the launch
+    extern __shared__ unsigned char smem_raw[];
+    const uint32_t base = (smem_u32(smem_raw) + 1023u) & ~1023u;
+    unsigned char* sm = smem_raw + (base - smem_u32(smem_raw));
+    uint64_t* bars = reinterpret_cast<uint64_t*>(sm + d_bar(NL));
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(sm + d_bar(NL) + 256);
+
+    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+    const int chunk = blockIdx.z;
+    Tile5Iter it;
+    it.I = a.rb_begin + blockIdx.x;
+    it.B = a.nblocks;
+    it.n = a.n;
+    const int per = (a.half + a.nsplits - 1) / a.nsplits;
+    it.k_begin = blockIdx.y * per;
+    it.ntiles = 4 * (min(a.half, it.k_begin + per) - it.k_begin);
+    if (it.ntiles < 0) it.ntiles = 0;
+    const int G = a.G, KS = a.KS;
+
+    if (tid == 0) {
+#pragma unroll
+        for (int s = 0; s < D_ZST; ++s) mbar_init(&bars[BD_ZFULL + s], 1);
+#pragma unroll
+        for (int b = 0; b < 2; ++b) {
+            mbar_init(&bars[BD_BFULL + b], 1);
+            mbar_init(&bars[BD_SFULL + b], D_AW / 2);
+            mbar_init(&bars[BD_TDONE + b], 2);
+            mbar_init(&bars[BD_EREAD + b], 4);
+            mbar_init(&bars[BD_D1EMPTY + b], D_AW);
+        }
+        mbar_init(&bars[BD_BCFULL], 1);
+        mbar_init(&bars[BD_AFULL], 1);
+#pragma unroll
+        for (int s = 0; s < 8; ++s) {
+            mbar_init(&bars[BD_D0FULL + s], 1);
+            mbar_init(&bars[BD_D0FREE + s], D_AW / 2);
+        }
+        mbar_fence_init();
+    }
+    if (warp == D_AW) {
+        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], 512;" ::"r"(smem_u32(tmem_slot)) : "memory");
+        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+    }
+    tc5_fence_before();
+    __syncthreads();
+    tc5_fence_after();
+    const uint32_t tmem = *tmem_slot;
+
+    if (warp < D_AW) {
+        // =========================================== arithmetic warps ===================================================
+        // two teams of eight warps take the tiles in turn (team = tile parity = S buffer), so that one team's exponentials fill the
+        // XU pipe while the other waits for its exponents, loads them, or splits and stores its S tile.  Inside a team: TMEM lane
+        // quadrant = warp & 3 (thread = row), half = which 16 of the tile's 32 columns.
+        asm volatile("setmaxnreg.inc.sync.aligned.u32 %0;" ::"n"(D_REGS_ARITH));
+        const int team = warp >> 3, half = (warp >> 2) & 1, part = 2 * team + half;
+        const int rtid = tid & (T5_ROWS - 1);
+        const long long row = (long long)it.I * T5_ROWS + rtid;
+        const bool valid = row < a.n;
+        const uint32_t lanes = (uint32_t)((warp & 3) * 32) << 16;  // this warp's TMEM lane quadrant
+        f32x2 acc[D_FC / 2], comp[D_FC / 2];
+#pragma unroll
+        for (int q = 0; q < D_FC / 2; ++q) { acc[q] = 0ull; comp[q] = 0ull; }
+
+        // every warp folds its rows' share (4 of the 16 right-hand sides) of a closed row-side epoch into the running total
+        auto fold_epoch = [&](int e) {
+            float d[D_FC], x[D_FC];
+            const uint32_t ta = tmem + D_TM_D1 + 32u * (uint32_t)(e & 1) + (uint32_t)(part * D_FC) + lanes;
+            tmem5_ld4(ta, d);            // Sh.Vh + Sl.Vh
+            tmem5_ld4(ta + 16u, x);      // Sh.Vl
+            tc5_fence_before();
+            __syncwarp();
+            if (lane == 0) mbar5_arrive(&bars[BD_D1EMPTY + (e & 1)]);
+#pragma unroll
+            for (int q = 0; q < D_FC / 2; ++q) {
+                const f32x2 y = sub2(pack2(d[2 * q] + x[2 * q], d[2 * q + 1] + x[2 * q + 1]), comp[q]);
+                const f32x2 tsum = add2(acc[q], y);
+                comp[q] = sub2(sub2(tsum, acc[q]), y);
+                acc[q] = tsum;
+            }
+        };
+
+        // D0 is handed over group by group: the team's item i = (tile, group) lives in the team's D0 buffer i % 4 (so the issuers
+        // run up to three groups ahead) and is released as soon as its exponents are in registers.  Two register sets: while the
+        // exponentials of item i are taken from one, the tcgen05.ld of item i+1 fills the other (tcgen05.wait::ld waits for ALL
+        // loads of the thread, so the next load is issued right after the wait for the current one).
+        uint32_t una[16], unb[16];
+#define TCD_LD16(arr, addr)                                                                                                            \
+    asm volatile("tcgen05.ld.sync.aligned.32x32b.x16.b32 {%0,%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15}, [%16];"             \
+                 : "=r"(arr[0]), "=r"(arr[1]), "=r"(arr[2]), "=r"(arr[3]), "=r"(arr[4]), "=r"(arr[5]), "=r"(arr[6]), "=r"(arr[7]),     \
+                   "=r"(arr[8]), "=r"(arr[9]), "=r"(arr[10]), "=r"(arr[11]), "=r"(arr[12]), "=r"(arr[13]), "=r"(arr[14]),              \
+                   "=r"(arr[15])                                                                                                       \
+                 : "r"(addr))
+#define TCD_WAIT16(arr)                                                                                                                \
+    asm volatile("tcgen05.wait::ld.sync.aligned;"                                                                                      \
+                 : "+r"(arr[0]), "+r"(arr[1]), "+r"(arr[2]), "+r"(arr[3]), "+r"(arr[4]), "+r"(arr[5]), "+r"(arr[6]), "+r"(arr[7]),     \
+                   "+r"(arr[8]), "+r"(arr[9]), "+r"(arr[10]), "+r"(arr[11]), "+r"(arr[12]), "+r"(arr[13]), "+r"(arr[14]),              \
+                   "+r"(arr[15])                                                                                                       \
+                 :                                                                                                                     \
+                 : "memory")
+#pragma unroll
+        for (int q = 0; q < 16; ++q) { una[q] = 0u; unb[q] = 0u; }
+
+        // the team's tiles: live index j = team, team + 2, ..
+        int nlive = 0;
+        for (int t = it.next_live(0); t < it.ntiles; t = it.next_live(t + 1)) ++nlive;
+        int t_c = it.next_live(0), j_c = 0, g_c = 0;            // current item: tile, its live index, group
+        if (team == 1 && t_c < it.ntiles) { t_c = it.next_live(t_c + 1); j_c = 1; }
+        int folded = 0;
+        uint32_t item = 0;                                       // this team's item counter: D0 buffer 4 team + item % 4
+        float s[16];
+#pragma unroll
+        for (int c = 0; c < 16; ++c) s[c] = 0.f;
+        const uint32_t d0_base = tmem + D_TM_D0 + (uint32_t)(half * 16) + lanes;
+
+        auto step = [&](auto par) {      // one item; its exponents are (being) loaded into register set `par` (= item & 1)
+            constexpr int P = decltype(par)::value;
+            uint32_t (&cur)[16] = P ? unb : una;
+            uint32_t (&nxt)[16] = P ? una : unb;
+            const uint32_t buf = (uint32_t)(4 * team) + (item & 3u);
+            TCD_WAIT16(cur);
+            tc5_fence_before();
+            __syncwarp();
+            if (lane == 0) mbar5_arrive(&bars[BD_D0FREE + buf]);
+            // the item after this one
+            int t_n = t_c, j_n = j_c, g_n = g_c + 1;
+            if (g_n == G) {
+                g_n = 0;
+                t_n = it.next_live(t_c + 1);
+                j_n = j_c + 1;
+                if (t_n < it.ntiles) { t_n = it.next_live(t_n + 1); j_n = j_c + 2; }
+            }
+            if (t_n < it.ntiles) {
+                const uint32_t nbuf = (uint32_t)(4 * team) + ((item + 1) & 3u);
+                mbar_wait(&bars[BD_D0FULL + nbuf], ((item + 1) >> 2) & 1u);
+                tc5_fence_after();
+                TCD_LD16(nxt, d0_base + 32u * nbuf);
+            }
+            // exponentials of this item
+            if (it.diag(t_c)) {     // a pair with itself: the exact exponent (no cancellation error on the dominant entries of K)
+                const long long c0 = it.col0(t_c) + half * 16;
+                const int jg = chunk * G + g_c;
+                const uint32_t nl = __float_as_uint(jg < a.J ? __ldg(a.nlc + jg) : D_PAD);
+#pragma unroll
+                for (int c = 0; c < 16; ++c)
+                    if (c0 + c == row) cur[c] = nl;
+            }
+#pragma unroll
+            for (int c = 0; c < 16; ++c) s[c] += ex2_ftz(-__uint_as_float(cur[c]));
+            if (g_c == G - 1) {    // the tile is complete: split and store S
+                const int b = team, j = j_c;
+                if (j >= 2) {   // tile j-2 has left the tensor core: S buffer b is free, and (the row issuer commits in tile order)
+                                // every epoch that ended at or before tile j-2 is closed
+                    mbar_wait(&bars[BD_TDONE + b], (uint32_t)(((j >> 1) - 1) & 1));
+                    tc5_fence_after();
+                    while ((folded + 1) * D_F <= j - 1) fold_epoch(folded++);
+                }
+                // SWIZZLE_128B_BASE32B (32-byte chunks ^ row % 4), row-local stores (padding rows / columns hold exact zeros: their
+                // exponent is >= D_PAD)
+                unsigned char* sc = sm + D_S + (uint32_t)b * 32768u;
+#pragma unroll
+                for (int qq = 0; qq < 4; ++qq) {
+                    const uint32_t q = (uint32_t)(half * 4 + qq);
+                    float4 h, l;
+                    h.x = tf32_hi5(s[4 * qq]); h.y = tf32_hi5(s[4 * qq + 1]); h.z = tf32_hi5(s[4 * qq + 2]); h.w = tf32_hi5(s[4 * qq + 3]);
+                    l.x = s[4 * qq] - h.x; l.y = s[4 * qq + 1] - h.y; l.z = s[4 * qq + 2] - h.z; l.w = s[4 * qq + 3] - h.w;
+                    const uint32_t off = (uint32_t)rtid * 128u + ((((q >> 1) ^ ((uint32_t)rtid & 3u)) << 5) | ((q & 1u) << 4));
+                    *reinterpret_cast<float4*>(sc + off) = h;
+                    *reinterpret_cast<float4*>(sc + 16384u + off) = l;
+                }
+                fence5_async_smem();
+                __syncwarp();
+                if (lane == 0) mbar5_arrive(&bars[BD_SFULL + b]);
+#pragma unroll
+                for (int c = 0; c < 16; ++c) s[c] = 0.f;
+            }
+            t_c = t_n; j_c = j_n; g_c = g_n;
+            ++item;
+        };
+
+        if (t_c < it.ntiles) {      // the first item's load, then items in pairs (even items use register set a, odd ones b)
+            mbar_wait(&bars[BD_D0FULL + 4 * team], 0u);
+            tc5_fence_after();
+            TCD_LD16(una, d0_base + 32u * (uint32_t)(4 * team));
+            while (true) {
+                step(std::integral_constant<int, 0>{});
+                if (t_c >= it.ntiles) break;
+                step(std::integral_constant<int, 1>{});
+                if (t_c >= it.ntiles) break;
+            }
+        }
+#undef TCD_LD16
+#undef TCD_WAIT16
+        const int j = nlive;
+        if (j > 0) {    // j = number of live tiles; the row issuer's last commit covers every earlier row-side MMA (the last two
+                        // tiles in order: a parity wait must not fall more than one phase behind its barrier)
+            if (j >= 2) mbar_wait(&bars[BD_TDONE + ((j - 2) & 1)], (uint32_t)(((j - 2) >> 1) & 1));
+            mbar_wait(&bars[BD_TDONE + ((j - 1) & 1)], (uint32_t)(((j - 1) >> 1) & 1));
+            tc5_fence_after();
+            const int epochs = (j + D_F - 1) / D_F;
+            while (folded < epochs) fold_epoch(folded++);
+            if (valid) {
+                double* dst = a.acc + row * T5_N + part * D_FC;
+#pragma unroll
+                for (int q = 0; q < D_FC / 2; ++q) {
+                    float x, y;
+                    unpack2(acc[q], x, y);
+                    atomicAdd(dst + 2 * q, (double)x);
+                    atomicAdd(dst + 2 * q + 1, (double)y);
+                }
+            }
+        }
+    } else if (warp < D_AW + 4) {
+        // =========================================== epilogue warps (+ bulk copies) =====================================
+        asm volatile("setmaxnreg.dec.sync.aligned.u32 %0;" ::"n"(D_REGS_EPI));
+        const int qd = warp - D_AW;                                // TMEM lane quadrant
+        const bool loader = (qd == 1 && lane == 0);
+        const unsigned char* bsplit = reinterpret_cast<const unsigned char*>(a.bsplit);
+        const unsigned char* bimg = a.bimg + (size_t)chunk * a.nblocks * 4 * NL * 8192;
+
+        // the loader runs ahead of the consumers: B images three deep, B tiles of V two deep
+        int tz = it.next_live(0), jz = 0, tb = tz, jb = 0;
+        auto load_z = [&]() {
+            const long long c0 = it.col0(tz);
+            const int zs = jz % D_ZST;
+            mbar_expect_tx(&bars[BD_ZFULL + zs], (uint32_t)NL * 8192u);
+            bulk_g2s(sm + d_bimg(NL) + (uint32_t)zs * NL * 8192u, bimg + (size_t)(c0 / T5_BN) * NL * 8192, (uint32_t)NL * 8192u, &bars[BD_ZFULL + zs]);
+            tz = it.next_live(tz + 1);
+            ++jz;
+        };
+        auto load_b = [&]() {
+            const long long c0 = it.col0(tb);
+            const int bs = jb & 1;
+            mbar_expect_tx(&bars[BD_BFULL + bs], 4096u);
+            bulk_g2s(sm + D_BT + (uint32_t)bs * 4096u, bsplit + (c0 / T5_BN) * 4096, 4096u, &bars[BD_BFULL + bs]);
+            tb = it.next_live(tb + 1);
+            ++jb;
+        };
+        if (loader && tz < it.ntiles) {   // (a CTA without tiles must not leave copies in flight)
+            mbar_expect_tx(&bars[BD_AFULL], (uint32_t)NL * 32768u);
+            bulk_g2s(sm + D_AIMG, a.aimg + ((size_t)chunk * a.nblocks + it.I) * NL * 32768, (uint32_t)NL * 32768u, &bars[BD_AFULL]);
+            mbar_expect_tx(&bars[BD_BCFULL], 16384u);
+            bulk_g2s(sm + D_BC, bsplit + (long long)it.I * 16384, 16384u, &bars[BD_BCFULL]);
+            for (int s = 0; s < D_ZST && tz < it.ntiles; ++s) load_z();
+            for (int s = 0; s < 2 && tb < it.ntiles; ++s) load_b();
+        }
+        __syncwarp();
+
+        int j = 0, jc = 0;
+        for (int t = it.next_live(0); t < it.ntiles; t = it.next_live(t + 1), ++j) {
+            const int b = j & 1;
+            const bool diag = it.diag(t);
+            mbar_wait_ns(a.sleep_ns, &bars[BD_TDONE + b], (uint32_t)((j >> 1) & 1));
+            tc5_fence_after();
+            if (loader) {   // tile j is through: its B-image stage, S buffer and B stage are free
+                if (tz < it.ntiles) load_z();
+                if (tb < it.ntiles) load_b();
+            }
+            __syncwarp();
+            // quadrants 0,1 hold the tf32-part rows of columns 0..15 / 16..31 (lanes 0..15), quadrants 2,3 the remainder rows
+            float* P = reinterpret_cast<float*>(sm + D_EPI) + (jc & 1) * 1024;
+            if (!diag) {
+                const uint32_t ta = tmem + D_TM_D2 + 32u * (uint32_t)b + ((uint32_t)(qd * 32) << 16);
+                float d[8], x[8], d2[8], x2[8];     // right-hand sides 0..7 | 8..15, [Vh part | Vl part] summed
+                if (!(a.diag & 32)) tmem5_ld8x4(ta, ta + 16u, ta + 8u, ta + 24u, d, x, d2, x2);
+                if (lane < 16) {
+                    float4* dst = reinterpret_cast<float4*>(P + qd * 256 + lane * 16);
+                    dst[0] = make_float4(d[0] + x[0], d[1] + x[1], d[2] + x[2], d[3] + x[3]);
+                    dst[1] = make_float4(d[4] + x[4], d[5] + x[5], d[6] + x[6], d[7] + x[7]);
+                    dst[2] = make_float4(d2[0] + x2[0], d2[1] + x2[1], d2[2] + x2[2], d2[3] + x2[3]);
+                    dst[3] = make_float4(d2[4] + x2[4], d2[5] + x2[5], d2[6] + x2[6], d2[7] + x2[7]);
+                }
+            }
+            tc5_fence_before();
+            __syncwarp();
+            if (lane == 0) mbar5_arrive(&bars[BD_EREAD + b]);
+            if (!diag) {
+                asm volatile("bar.sync 1, 128;" ::: "memory");
+                const int et = tid - 32 * D_AW, c = et & 15;
+                const long long c0 = it.col0(t);
+#pragma unroll
+                for (int k = 0; k < 4; ++k) {
+                    const int rr = (et >> 4) + 8 * k;      // tile column 0..31 = output row c0 + rr
+                    const float v = P[(rr >> 4) * 256 + (rr & 15) * 16 + c] + P[(2 + (rr >> 4)) * 256 + (rr & 15) * 16 + c];
+                    if (c0 + rr < a.n && !(a.diag & 1)) atomicAdd(a.acc + (c0 + rr) * T5_N + c, (double)v);
+                }
+                ++jc;
+            }
+        }
+    } else {
+        // =========================================== MMA issuers (lane 0 of one warp each) ==============================
+        // a UTCHMMA blocks its issuing warp ~150 clk whatever its size, so every stream of MMAs has a warp of its own and none of
+        // them does anything else: role 0 row side, roles 1/2 column side (tile rows 0..63 / 64..127), roles 3.. distances
+        asm volatile("setmaxnreg.dec.sync.aligned.u32 %0;" ::"n"(D_REGS_ISSUE));
+        const int role = warp - D_AW - 4;
+        const bool has_tiles = it.next_live(0) < it.ntiles;
+        if (lane == 0 && has_tiles && role == 0) {
+            constexpr uint32_t IDESC_ROW_N32 = idesc5_tf32(128, 2 * T5_N, 0, 0), IDESC_ROW_N16 = idesc5_tf32(128, T5_N, 0, 0);
+            int j = 0;
+            for (int t = it.next_live(0); t < it.ntiles; t = it.next_live(t + 1), ++j) {   // D1 += Sh.[Vh|Vl] + Sl.Vh, four k-steps of 8 tile columns
+                const int b = j & 1, e = j / D_F;
+                mbar_wait_ns(a.sleep_ns, &bars[BD_BFULL + b], (uint32_t)((j >> 1) & 1));
+                if (j % D_F == 0 && e >= 2) mbar_wait_ns(a.sleep_ns, &bars[BD_D1EMPTY + (e & 1)], (uint32_t)(((e >> 1) - 1) & 1));
+                mbar_wait_ns(a.sleep_ns, &bars[BD_SFULL + b], (uint32_t)((j >> 1) & 1));
+                tc5_fence_after();
+                const uint32_t sbuf = base + D_S + (uint32_t)b * 32768u;
+                const uint32_t d1 = tmem + D_TM_D1 + 32u * (uint32_t)(e & 1);
+                const uint64_t dA_h = smem_desc5(sbuf, 512, 512, LAYOUT5_SW128_BASE32B);
+                const uint64_t dA_l = smem_desc5(sbuf + 16384u, 512, 512, LAYOUT5_SW128_BASE32B);
+                const uint64_t dB = smem_desc5(base + D_BT + (uint32_t)b * 4096u, 16, 1024, LAYOUT5_SW128);
+#pragma unroll
+                for (int ks = 0; ks < 4; ++ks) {
+                    if (a.diag & 4) break;
+                    umma5(d1, dA_h + (uint64_t)(ks * 2), dB + (uint64_t)(ks * 2), IDESC_ROW_N32, (j % D_F != 0 || ks > 0) ? 1u : 0u);
+                    umma5(d1, dA_l + (uint64_t)(ks * 2), dB + (uint64_t)(ks * 2), IDESC_ROW_N16, 1u);
+                }
+                umma5_commit(&bars[BD_TDONE + b]);
+            }
+        } else if (lane == 0 && has_tiles && role == 1) {
+            constexpr uint32_t IDESC_COL = idesc5_tf32(64, 2 * T5_N, 1, 0);
+            mbar_wait_ns(a.sleep_ns, &bars[BD_BCFULL], 0u);
+            int j = 0;
+            for (int t = it.next_live(0); t < it.ntiles; t = it.next_live(t + 1), ++j) {   // D2 = [Sh ; Sl]^T . [Vh|Vl], sixteen k-steps of 8 tile rows
+                const int b = j & 1;
+                if (j >= 2) mbar_wait_ns(a.sleep_ns, &bars[BD_EREAD + b], (uint32_t)(((j >> 1) - 1) & 1));        // D2[b] has been read
+                mbar_wait_ns(a.sleep_ns, &bars[BD_SFULL + b], (uint32_t)((j >> 1) & 1));
+                tc5_fence_after();
+                if (!it.diag(t) && !(a.diag & 2)) {      // (nothing to do on the diagonal block)
+                    const uint32_t d2 = tmem + D_TM_D2 + 32u * (uint32_t)b;
+                    const uint64_t dA = smem_desc5(base + D_S + (uint32_t)b * 32768u, 16384, 512, LAYOUT5_SW128_BASE32B);
+                    const uint64_t dB = smem_desc5(base + D_BC, 16, 1024, LAYOUT5_SW128);
+#pragma unroll
+                    for (int g = 0; g < 16; ++g)
+                        umma5(d2, dA + (uint64_t)((g * 1024) >> 4), dB + (uint64_t)(((g >> 2) * 4096 + (g & 3) * 32) >> 4), IDESC_COL, g > 0 ? 1u : 0u);
+                }
+                umma5_commit(&bars[BD_TDONE + b]);
+            }
+        } else if (lane == 0 && has_tiles && role - 2 < D_NDI) {
+            // issuer w owns the groups w, w + D_NDI, .. of every batch: U = Ah.Bh + Al.Bh + Ah.Bl into the batch's D0 columns, KS k-steps each
+            const int w = role - 2;
+            constexpr uint32_t IDESC_D0 = idesc5_tf32(128, T5_BN, 0, 0);
+            mbar_wait_ns(a.sleep_ns, &bars[BD_AFULL], 0u);
+            int jd = 0;
+            uint32_t items[2] = {0u, 0u};      // per team: (tile, batch) counter
+            for (int t = it.next_live(0); t < it.ntiles; t = it.next_live(t + 1), ++jd) {
+                const int zs = jd % D_ZST, team = jd & 1;
+                mbar_wait_ns(a.sleep_ns, &bars[BD_ZFULL + zs], (uint32_t)((jd / D_ZST) & 1));
+                tc5_fence_after();
+                const uint32_t bst = base + d_bimg(NL) + (uint32_t)zs * NL * 8192u;
+                for (int g = 0; g < G; ++g) {
+                    const uint32_t item = items[team]++;
+                    if ((g & 1) != w) continue;          // the two issuers take the groups in turn
+                    const uint32_t buf = (uint32_t)(4 * team) + (item & 3u), use = item >> 2;
+                    if (use >= 1) {
+                        mbar_wait_ns(a.sleep_ns, &bars[BD_D0FREE + buf], (use - 1) & 1u);
+                        tc5_fence_after();
+                    }
+                    const uint32_t d0 = tmem + D_TM_D0 + 32u * buf;
+                    for (int ks = 0; ks < ((a.diag & 8) ? 0 : KS); ++ks) {
+                        const int ksi = g * KS + ks;
+                        const uint32_t l = (uint32_t)(ksi >> 2);
+                        const uint64_t o = (uint64_t)((ksi & 3) * 2);
+                        const uint64_t dAh = smem_desc5(base + D_AIMG + l * 32768u, 16, 1024, LAYOUT5_SW128) + o;
+                        const uint64_t dAl = smem_desc5(base + D_AIMG + l * 32768u + 16384u, 16, 1024, LAYOUT5_SW128) + o;
+                        const uint64_t dBh = smem_desc5(bst + l * 8192u, 16, 1024, LAYOUT5_SW128) + o;
+                        const uint64_t dBl = smem_desc5(bst + l * 8192u + 4096u, 16, 1024, LAYOUT5_SW128) + o;
+                        umma5(d0, dAh, dBh, IDESC_D0, ks > 0 ? 1u : 0u);
+                        umma5(d0, dAl, dBh, IDESC_D0, 1u);
+                        umma5(d0, dAh, dBl, IDESC_D0, 1u);
+                    }
+                    umma5_commit(&bars[BD_D0FULL + buf]);
+                }
+            }
+        }
+        __syncwarp();
+    }
+    tc5_fence_before();
+    __syncthreads();
+    if (warp == D_AW) {
+        asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, 512;" ::"r"(tmem) : "memory");
+    }
+}
+
+// ---- operand images ---------------------------------------------------------------------------------------------------------
+// column sums of the packed coordinates (for centring): sums[chunk*CP + q] += sum over a slab of rows
+__global__ void tcd_colsum_kernel(const float* __restrict__ zp, long long n, int CP, int nchunks, double* __restrict__ sums) {
+    __shared__ double red[8][33];
+    const int q = threadIdx.x, chunk = blockIdx.y;
+    double acc = 0.0;
+    if (q < CP)
+        for (long long r = (long long)blockIdx.x * blockDim.y + threadIdx.y; r < n; r += (long long)gridDim.x * blockDim.y)
+            acc += (double)__ldg(zp + ((long long)chunk * n + r) * CP + q);
+    red[threadIdx.y][q] = acc;
+    __syncthreads();
+    if (threadIdx.y == 0 && q < CP) {
+        for (int y = 1; y < 8; ++y) acc += red[y][q];
+        atomicAdd(sums + chunk * CP + q, acc);
+    }
+}
+
+// one thread per (row, chunk, k-step of a 128-byte line): 8 floats of the A line and 8 of the B line, split and swizzled
+__global__ void tcd_build_images_kernel(const float* __restrict__ zp, long long n, long long n_pad, Layout lay, const float* __restrict__ nlc,
+                                        const double* __restrict__ colsum, int GT, int KS, int NL, int nch, unsigned char* __restrict__ aimg,
+                                        unsigned char* __restrict__ bimg, unsigned* __restrict__ gate) {
+    const long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    const int nks = 4 * NL;
+    const long long per_chunk = n_pad * nks;
+    float maxsq = 0.f;
+    if (idx < per_chunk * nch) {
+        const int chunk = (int)(idx / per_chunk);
+        const long long rem = idx - (long long)chunk * per_chunk;
+        const int ksi = (int)(rem / n_pad);             // consecutive threads = consecutive rows
+        const long long row = rem - (long long)ksi * n_pad;
+        const int g = ksi / KS, ks = ksi - g * KS, jg = chunk * GT + g, K = lay.K;
+        float A[8], B[8];
+#pragma unroll
+        for (int e = 0; e < 8; ++e) { A[e] = 0.f; B[e] = 0.f; }
+        if (g < GT) {
+            const bool live = row < n && jg < lay.J;
+            if (live) {
+                const int lc = jg / lay.G, off = (jg % lay.G) * lay.KP;      // the group's chunk and offset in the packed layout
+                const float* src = zp + ((long long)lc * n + row) * lay.CP + off;
+                const double* mu = colsum + lc * lay.CP + off;
+                const double inv_n = 1.0 / (double)n;
+                double sq = 0.0;
+#pragma unroll
+                for (int e = 0; e < 6; ++e) {
+                    const int m = 6 * ks + e;
+                    if (m < K) {
+                        const float z = (float)((double)__ldg(src + m) - mu[m] * inv_n);
+                        A[e] = -2.f * z;
+                        B[e] = z;
+                        sq += (double)z * (double)z;
+                    }
+                }
+                const float sqf = (float)sq;
+                A[6] = ks == 0 ? fminf(sqf + __ldg(nlc + jg), D_PAD) : sqf;
+                B[6] = 1.f;
+                A[7] = 1.f;
+                B[7] = sqf;
+                if (ks == 0) {      // the whole group's squared norm decides whether the tensor-core distances are accurate enough
+                    double tot = 0.0;
+                    for (int m = 0; m < K; ++m) { const double z = (double)__ldg(src + m) - mu[m] * inv_n; tot += z * z; }
+                    maxsq = (float)tot;
+                }
+            } else if (ks == 0) {   // padding rows / columns / groups: exponent >= D_PAD, i.e. an exact zero
+                A[6] = D_PAD; B[6] = 1.f; A[7] = 1.f; B[7] = D_PAD;
+            }
+        }
+        float4 Ah[2], Al[2], Bh[2], Bl[2];
+        float* pAh = reinterpret_cast<float*>(Ah); float* pAl = reinterpret_cast<float*>(Al);
+        float* pBh = reinterpret_cast<float*>(Bh); float* pBl = reinterpret_cast<float*>(Bl);
+#pragma unroll
+        for (int e = 0; e < 8; ++e) {   // round-to-nearest split (a truncating split biases U by ~3e-7 |z|^2: tools/tcd_check.py adv)
+            pAh[e] = tf32_rn(A[e]); pAl[e] = tf32_rn(A[e] - pAh[e]);
+            pBh[e] = tf32_rn(B[e]); pBl[e] = tf32_rn(B[e] - pBh[e]);
+        }
+        const int l = ksi >> 2;
+        const uint32_t c16 = (uint32_t)(ksi & 3) * 2u;
+        const long long nblocks = n_pad / T5_ROWS;
+        {
+            const uint32_t r = (uint32_t)(row & 127);
+            unsigned char* dst = aimg + (((size_t)chunk * nblocks + (row >> 7)) * NL + l) * 32768 + (size_t)r * 128;
+#pragma unroll
+            for (int hh = 0; hh < 2; ++hh) {
+                const uint32_t off = ((c16 + hh) ^ (r & 7u)) << 4;
+                *reinterpret_cast<float4*>(dst + off) = Ah[hh];
+                *reinterpret_cast<float4*>(dst + 16384 + off) = Al[hh];
+            }
+        }
+        {
+            const uint32_t r = (uint32_t)(row & 31);
+            unsigned char* dst = bimg + (((size_t)chunk * nblocks * 4 + (row >> 5)) * NL + l) * 8192 + (size_t)r * 128;
+#pragma unroll
+            for (int hh = 0; hh < 2; ++hh) {
+                const uint32_t off = ((c16 + hh) ^ (r & 7u)) << 4;
+                *reinterpret_cast<float4*>(dst + off) = Bh[hh];
+                *reinterpret_cast<float4*>(dst + 4096 + off) = Bl[hh];
+            }
+        }
+    }
+    double sum4 = (double)maxsq * (double)maxsq;
+#pragma unroll
+    for (int off = 16; off > 0; off >>= 1) {
+        maxsq = fmaxf(maxsq, __shfl_xor_sync(0xffffffffu, maxsq, off));
+        sum4 += __shfl_xor_sync(0xffffffffu, sum4, off);
+    }
+    if ((threadIdx.x & 31) == 0 && maxsq > 0.f) {
+        atomicMax(gate, __float_as_uint(maxsq));
+        atomicAdd(reinterpret_cast<double*>(gate + 2), sum4);
+    }
+}
+
+// ---- host side ----------------------------------------------------------------------------------------------------------------
+TcdPlan plan_tcd(const Layout& lay) {
+    TcdPlan p;
+    std::memset(&p, 0, sizeof(p));
+    static const int enabled = [] { const char* e = getenv("RPGP_SYM_TCD"); return e ? atoi(e) : 1; }();
+    static const int kmin = [] { const char* e = getenv("RPGP_SYM_TCD_KMIN"); return e ? atoi(e) : 4; }();
+    if (!enabled || lay.K < kmin || lay.K > 24) return p;
+    p.KS = (lay.K + 5) / 6;       // six coordinates + their two partial norms per k-step of eight
+    const int gmax = 8 / p.KS;
+    p.nchunks = (lay.J + gmax - 1) / gmax;
+    p.GT = (lay.J + p.nchunks - 1) / p.nchunks;
+    p.NL = (p.GT * p.KS + 3) / 4;
+    p.NB = (p.GT + 1) / 2;
+    p.GB = 2;
+    p.supported = 1;
+    return p;
+}
+
+size_t tcd_workspace_bytes(long long n, const Layout& lay) {
+    const TcdPlan p = plan_tcd(lay);
+    if (!p.supported) return 0;
+    const size_t nblocks = (size_t)((n + T5_ROWS - 1) / T5_ROWS);
+    return D_WS_HEADER + 2 * (size_t)p.nchunks * nblocks * p.NL * 32768;
+}
+
+TcdGate tcd_gate(long long n, const Layout& lay) {
+    // norm-wise error model (profiles/tcd_accuracy_r01.txt): a row whose centred, scaled squared group norm is r2 carries a relative
+    // error ~ 2..3.5e-8 * r2 on its near pairs, so ||error|| / ||K.V|| <~ 3.5e-8 * sqrt(mean r2^2): bound the root mean square of the
+    // squared norms, and cap single rows at 10x that
+    TcdGate g;
+    const float b = tcd_gate_bound(), cap = 10.f * b;
+    std::memcpy(&g.max_bits, &cap, sizeof(float));
+    g.sum4_max = (double)b * (double)b * (double)n * (double)lay.J;
+    return g;
+}
+
+float tcd_gate_bound() {
+    // largest scaled, centred squared group norm for which U from the tensor core keeps K.V inside 1e-5 even when every pair that
+    // matters sits at that radius (measured: tools/tcd_check.py adv, profiles/tcd_accuracy_r01.txt)
+    static const float bound = [] { const char* e = getenv("RPGP_SYM_TCD_AMAX"); return e ? (float)atof(e) : 200.f; }();
+    return bound;
+}
+
+int launch_sym_tcd(const float* zp, long long n, const Layout& lay, const float* nlc, const float* bsplit, double* acc, int nblocks,
+                   int rb_begin, int nrb, void* ws, size_t ws_bytes, const unsigned** gate_out, cudaStream_t st) {
+    const TcdPlan p = plan_tcd(lay);
+    if (!p.supported) return ERR_UNSUPPORTED;
+    const size_t img_bytes = (size_t)p.nchunks * nblocks * p.NL * 32768;
+    if (ws == nullptr || ws_bytes < D_WS_HEADER + 2 * img_bytes) {
+        set_error("mvm_sym: distance-image workspace %zu bytes < required %zu", ws_bytes, D_WS_HEADER + 2 * img_bytes);
+        return ERR_WORKSPACE;
+    }
+    unsigned* gate = (unsigned*)ws;
+    double* colsum = (double*)((unsigned char*)ws + 1024);
+    unsigned char* aimg = (unsigned char*)ws + D_WS_HEADER;
+    unsigned char* bimg = aimg + img_bytes;
+    if ((size_t)lay.nchunks * lay.CP * sizeof(double) > D_WS_HEADER - 1024) return ERR_UNSUPPORTED;
+    RPGP_CUDA_OK(cudaMemsetAsync(gate, 0, D_WS_HEADER, st));
+    tcd_colsum_kernel<<<dim3((unsigned)std::min<long long>((n + 7) / 8, 1184), (unsigned)lay.nchunks), dim3(32, 8), 0, st>>>(zp, n, lay.CP, lay.nchunks, colsum);
+    note_launch();
+    RPGP_CUDA_OK(cudaGetLastError());
+    const long long n_pad = (long long)nblocks * T5_ROWS;
+    const long long total = n_pad * 4 * p.NL * p.nchunks;
+    tcd_build_images_kernel<<<(unsigned)((total + 255) / 256), 256, 0, st>>>(zp, n, n_pad, lay, nlc, colsum, p.GT, p.KS, p.NL, p.nchunks, aimg, bimg,
+                                                                             gate);
+    note_launch();
+    RPGP_CUDA_OK(cudaGetLastError());
+
+    SymDArgs a;
+    a.aimg = aimg; a.bimg = bimg; a.bsplit = bsplit; a.nlc = nlc; a.acc = acc; a.gate = gate;
+    const TcdGate gb = tcd_gate(n, lay);
+    a.gate_max = gb.max_bits;
+    a.gate_sum4_max = gb.sum4_max;
+    a.n = n; a.nblocks = nblocks; a.half = nblocks / 2 + 1; a.rb_begin = rb_begin;
+    a.G = p.GT; a.KS = p.KS; a.NB = p.NB; a.GB = p.GB; a.J = lay.J;
+    static const int diag_env = [] { const char* e = getenv("RPGP_TCD_DIAG"); return e ? atoi(e) : 0; }();
+    a.diag = diag_env;
+    static const int sleep_env = [] { const char* e = getenv("RPGP_TCD_SLEEP"); return e ? atoi(e) : D_SLEEP; }();
+    a.sleep_ns = sleep_env;
+    static const int dbg_env = [] { const char* e = getenv("RPGP_TCD_DBG"); return e ? atoi(e) : 0; }();
+    a.dbg = nullptr;
+    if (dbg_env) {
+        RPGP_CUDA_OK(cudaMalloc(&a.dbg, 64 * 12 * sizeof(long long)));
+        RPGP_CUDA_OK(cudaMemset(a.dbg, 0, 64 * 12 * sizeof(long long)));
+    }
+    static const int splits_env = [] { const char* e = getenv("RPGP_SYM_SPLITS"); return e ? atoi(e) : 0; }();
+    long long want = (148LL * 16 + (long long)nrb * p.nchunks - 1) / ((long long)nrb * p.nchunks);
+    if (splits_env > 0) want = splits_env;
+    want = std::max<long long>(1, std::min<long long>(want, a.half));
+    a.nsplits = (int)want;
+    dim3 grid((unsigned)nrb, (unsigned)a.nsplits, (unsigned)p.nchunks);
+    cudaError_t e;
+    if (p.NL == 1) {
+        e = cudaFuncSetAttribute(mvm_sym_tcd_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)d_smem_bytes(1));
+        if (e != cudaSuccess) return cuda_fail(e, "cudaFuncSetAttribute(mvm_sym_tcd_kernel<1>)");
+        mvm_sym_tcd_kernel<1><<<grid, D_THREADS, d_smem_bytes(1), st>>>(a);
+    } else {
+        e = cudaFuncSetAttribute(mvm_sym_tcd_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)d_smem_bytes(2));
+        if (e != cudaSuccess) return cuda_fail(e, "cudaFuncSetAttribute(mvm_sym_tcd_kernel<2>)");
+        mvm_sym_tcd_kernel<2><<<grid, D_THREADS, d_smem_bytes(2), st>>>(a);
+    }
+    note_launch();
+    *gate_out = gate;
+    if (a.dbg) {   // debugging aid only: synchronises and prints the stamps relative to the first one
+        long long h[64 * 12];
+        RPGP_CUDA_OK(cudaStreamSynchronize(st));
+        RPGP_CUDA_OK(cudaMemcpy(h, a.dbg, sizeof(h), cudaMemcpyDeviceToHost));
+        cudaFree(a.dbg);
+        fprintf(stderr, "tile: arith start | D0 read+exp | SFULL || row: before SFULL wait | after | committed || epi: TDONE seen | done\n");
+        for (int j = 0; j < 20; ++j) {
+            fprintf(stderr, "%2d:", j);
+            for (int k = 0; k < 3; ++k) fprintf(stderr, " %8lld", h[j * 12 + k] ? h[j * 12 + k] - h[0] : -1);
+            fprintf(stderr, "\n");
+        }
+    }
+    return cuda_fail(cudaGetLastError(), "mvm_sym_tcd_kernel launch");
+}
+
+}  // namespace rpgp
