@@ -46,11 +46,13 @@ using namespace tcdev;
 constexpr int D_F = 4;            // tiles accumulated in TMEM per row-side epoch
 constexpr int D_ZST = 3;          // B-image stages
 constexpr int D_AW = 16;          // arithmetic warps
-constexpr int D_NPART = 4;        // column quarters of a tile
-constexpr int D_FC = T5_N / D_NPART;   // right-hand-side columns folded per arithmetic thread
+constexpr int D_FC = 4;            // right-hand-side columns folded per arithmetic thread (16 warps: 4 lane quadrants x 4 column parts)
 constexpr int D_NDI = 2;          // distance-MMA issuing warps (one per group of a batch)
 constexpr int D_ISSUERS = 2 + D_NDI; // row side, column side, distances
 constexpr int D_THREADS = 32 * (D_AW + 4 + D_ISSUERS);
+#ifndef TCD_DIAG
+#define TCD_DIAG 0                 // diagnostic builds only (tools/tcd_diag.sh): 1 no column atomics, 2 no column MMAs, 4 no row MMAs,
+#endif                             // 8 no distance MMAs, 32 no D2 reads; -DTCD_DEBUG_STAMPS adds clock64 stamps of one CTA (RPGP_TCD_DBG=1 prints them)
 #ifndef TCD_SLEEP_NS
 #define TCD_SLEEP_NS 64
 #endif
@@ -140,15 +142,18 @@ struct SymDArgs {
     double gate_sum4_max;
     long long n;
     int nblocks, half, nsplits, rb_begin;
-    int G, KS, NB, GB, J;        // groups per chunk, k-steps per group, D0 batches per tile, groups per batch (<= 4), total groups
+    int G, KS, NB, J;            // groups per chunk, k-steps per group, D0 batches (of two groups) per tile, total groups
     long long* dbg;              // RPGP_TCD_DBG: clock64 stamps of CTA (0,0,0), [64 tiles][8]
     int sleep_ns;                // back-off of the helper warps' barrier polls
-    int diag;                    // diagnostics (RPGP_TCD_DIAG): 1 no column atomics, 2 no column MMAs, 4 no row MMAs, 8 no distance MMAs, 32 no D2 reads
 };
 
 }  // namespace
 
+#ifdef TCD_DEBUG_STAMPS
 #define TCD_STAMP(j, k) do { if (a.dbg && (j) < 64 && blockIdx.x == 7 && blockIdx.y == 0 && blockIdx.z == 0) a.dbg[(j) * 12 + (k)] = clock64(); } while (0)
+#else
+#define TCD_STAMP(j, k) do { } while (0)
+#endif
 
 template <int NL>
 __global__ void __maxnreg__(80) mvm_sym_tcd_kernel(const SymDArgs a) {
@@ -169,7 +174,7 @@ __global__ void __maxnreg__(80) mvm_sym_tcd_kernel(const SymDArgs a) {
     it.k_begin = blockIdx.y * per;
     it.ntiles = 4 * (min(a.half, it.k_begin + per) - it.k_begin);
     if (it.ntiles < 0) it.ntiles = 0;
-    const int G = a.G, KS = a.KS, NB = a.NB, GB = a.GB;
+    const int G = a.G, KS = a.KS, NB = a.NB;
 
     if (tid == 0) {
 #pragma unroll
@@ -389,7 +394,7 @@ __global__ void __maxnreg__(80) mvm_sym_tcd_kernel(const SymDArgs a) {
             if (!diag) {
                 const uint32_t ta = tmem + D_TM_D2 + 32u * (uint32_t)b + ((uint32_t)(qd * 32) << 16);
                 float d[8], x[8], d2[8], x2[8];     // right-hand sides 0..7 | 8..15, [Vh part | Vl part] summed
-                if (!(a.diag & 32)) tmem5_ld8x4(ta, ta + 16u, ta + 8u, ta + 24u, d, x, d2, x2);
+                if (!(TCD_DIAG & 32)) tmem5_ld8x4(ta, ta + 16u, ta + 8u, ta + 24u, d, x, d2, x2);
                 if (lane < 16) {
                     float4* dst = reinterpret_cast<float4*>(P + qd * 256 + lane * 16);
                     dst[0] = make_float4(d[0] + x[0], d[1] + x[1], d[2] + x[2], d[3] + x[3]);
@@ -409,7 +414,7 @@ __global__ void __maxnreg__(80) mvm_sym_tcd_kernel(const SymDArgs a) {
                 for (int k = 0; k < 4; ++k) {
                     const int rr = (et >> 4) + 8 * k;      // tile column 0..31 = output row c0 + rr
                     const float v = P[(rr >> 4) * 256 + (rr & 15) * 16 + c] + P[(2 + (rr >> 4)) * 256 + (rr & 15) * 16 + c];
-                    if (c0 + rr < a.n && !(a.diag & 1)) atomicAdd(a.acc + (c0 + rr) * T5_N + c, (double)v);
+                    if (c0 + rr < a.n && !(TCD_DIAG & 1)) atomicAdd(a.acc + (c0 + rr) * T5_N + c, (double)v);
                 }
                 ++jc;
             }
@@ -436,7 +441,7 @@ __global__ void __maxnreg__(80) mvm_sym_tcd_kernel(const SymDArgs a) {
                 const uint64_t dB = smem_desc5(base + D_BT + (uint32_t)b * 4096u, 16, 1024, LAYOUT5_SW128);
 #pragma unroll
                 for (int ks = 0; ks < 4; ++ks) {
-                    if (a.diag & 4) break;
+                    if (TCD_DIAG & 4) break;
                     umma5(d1, dA_h + (uint64_t)(ks * 2), dB + (uint64_t)(ks * 2), IDESC_ROW_N32, (j % D_F != 0 || ks > 0) ? 1u : 0u);
                     umma5(d1, dA_l + (uint64_t)(ks * 2), dB + (uint64_t)(ks * 2), IDESC_ROW_N16, 1u);
                 }
@@ -451,7 +456,7 @@ __global__ void __maxnreg__(80) mvm_sym_tcd_kernel(const SymDArgs a) {
                 if (j >= 2) mbar_wait_ns(a.sleep_ns, &bars[BD_EREAD + b], (uint32_t)(((j >> 1) - 1) & 1));        // D2[b] has been read
                 mbar_wait_ns(a.sleep_ns, &bars[BD_SFULL + b], (uint32_t)((j >> 1) & 1));
                 tc5_fence_after();
-                if (!it.diag(t) && !(a.diag & 2)) {      // (nothing to do on the diagonal block)
+                if (!it.diag(t) && !(TCD_DIAG & 2)) {      // (nothing to do on the diagonal block)
                     const uint32_t d2 = tmem + D_TM_D2 + 32u * (uint32_t)b;
                     const uint64_t dA = smem_desc5(base + D_S + (uint32_t)b * 32768u, 16384, 512, LAYOUT5_SW128_BASE32B);
                     const uint64_t dB = smem_desc5(base + D_BC, 16, 1024, LAYOUT5_SW128);
@@ -483,7 +488,7 @@ __global__ void __maxnreg__(80) mvm_sym_tcd_kernel(const SymDArgs a) {
                     }
                     if (g < G) {
                         const uint32_t d0 = tmem + D_TM_D0 + 64u * buf + 32u * (uint32_t)w;
-                        for (int ks = 0; ks < ((a.diag & 8) ? 0 : KS); ++ks) {
+                        for (int ks = 0; ks < ((TCD_DIAG & 8) ? 0 : KS); ++ks) {
                             const int ksi = g * KS + ks;
                             const uint32_t l = (uint32_t)(ksi >> 2);
                             const uint64_t o = (uint64_t)((ksi & 3) * 2);
@@ -693,17 +698,17 @@ int launch_sym_tcd(const float* zp, long long n, const Layout& lay, const float*
     a.gate_max = gb.max_bits;
     a.gate_sum4_max = gb.sum4_max;
     a.n = n; a.nblocks = nblocks; a.half = nblocks / 2 + 1; a.rb_begin = rb_begin;
-    a.G = p.GT; a.KS = p.KS; a.NB = p.NB; a.GB = p.GB; a.J = lay.J;
-    static const int diag_env = [] { const char* e = getenv("RPGP_TCD_DIAG"); return e ? atoi(e) : 0; }();
-    a.diag = diag_env;
+    a.G = p.GT; a.KS = p.KS; a.NB = p.NB; a.J = lay.J;
     static const int sleep_env = [] { const char* e = getenv("RPGP_TCD_SLEEP"); return e ? atoi(e) : D_SLEEP; }();
     a.sleep_ns = sleep_env;
-    static const int dbg_env = [] { const char* e = getenv("RPGP_TCD_DBG"); return e ? atoi(e) : 0; }();
     a.dbg = nullptr;
+#ifdef TCD_DEBUG_STAMPS
+    static const int dbg_env = [] { const char* e = getenv("RPGP_TCD_DBG"); return e ? atoi(e) : 0; }();
     if (dbg_env) {
         RPGP_CUDA_OK(cudaMalloc(&a.dbg, 64 * 12 * sizeof(long long)));
         RPGP_CUDA_OK(cudaMemset(a.dbg, 0, 64 * 12 * sizeof(long long)));
     }
+#endif
     static const int splits_env = [] { const char* e = getenv("RPGP_SYM_SPLITS"); return e ? atoi(e) : 0; }();
     long long want = (148LL * 16 + (long long)nrb * p.nchunks - 1) / ((long long)nrb * p.nchunks);
     if (splits_env > 0) want = splits_env;
@@ -722,18 +727,20 @@ int launch_sym_tcd(const float* zp, long long n, const Layout& lay, const float*
     }
     note_launch();
     *gate_out = gate;
+#ifdef TCD_DEBUG_STAMPS
     if (a.dbg) {   // debugging aid only: synchronises and prints the stamps relative to the first one
         long long h[64 * 12];
         RPGP_CUDA_OK(cudaStreamSynchronize(st));
         RPGP_CUDA_OK(cudaMemcpy(h, a.dbg, sizeof(h), cudaMemcpyDeviceToHost));
         cudaFree(a.dbg);
-        fprintf(stderr, "tile: arith start | D0 read+exp | SFULL || row: before SFULL wait | after | committed || epi: TDONE seen | done\n");
+        fprintf(stderr, "live tile: arithmetic start | exponentials done | SFULL   (clk since the first stamp; team = tile parity)\n");
         for (int j = 0; j < 20; ++j) {
             fprintf(stderr, "%2d:", j);
             for (int k = 0; k < 3; ++k) fprintf(stderr, " %8lld", h[j * 12 + k] ? h[j * 12 + k] - h[0] : -1);
             fprintf(stderr, "\n");
         }
     }
+#endif
     return cuda_fail(cudaGetLastError(), "mvm_sym_tcd_kernel launch");
 }
 

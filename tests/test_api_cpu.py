@@ -222,3 +222,29 @@ def test_priors_and_constraints():
     assert abs(gpytorch.likelihoods.GaussianLikelihood().noise.item() - (np.log(2) + 1e-4)) < 1e-6
     m = gpytorch.means.ConstantMean()
     assert m(torch.randn(4, 3)).shape == (4,) and m.constant.item() == 0
+
+
+def test_distance_on_tensor_core_plan_and_base_layouts():
+    """host-side planning that needs no GPU: the chunking of the K > 1 tensor-core-distance path (csrc/sym_tcd.cu: six coordinates +
+    two partial norms per k-step of eight, at most eight k-steps per chunk) and the layouts of the non-RBF base kernels"""
+    from rpgp import _lib
+    plan = _lib.mvm_sym_distance_plan(_lib.plan_layout(20, 5))
+    assert plan == dict(groups_per_chunk=7, ksteps_per_group=1, lines=2, nchunks=3, bound=plan["bound"]) and plan["bound"] > 0
+    plan = _lib.mvm_sym_distance_plan(_lib.plan_layout(1, 20))
+    assert (plan["groups_per_chunk"], plan["ksteps_per_group"], plan["lines"], plan["nchunks"]) == (1, 4, 1, 1)
+    plan = _lib.mvm_sym_distance_plan(_lib.plan_layout(8, 6))
+    assert (plan["groups_per_chunk"], plan["ksteps_per_group"], plan["lines"], plan["nchunks"]) == (8, 1, 2, 1)
+    plan = _lib.mvm_sym_distance_plan(_lib.plan_layout(5, 12))
+    assert (plan["groups_per_chunk"], plan["ksteps_per_group"], plan["lines"], plan["nchunks"]) == (3, 2, 2, 2)
+    for J, K in [(20, 1), (10, 3), (1, 30)]:          # K = 1, K below the cross-over, K too wide: direct differences only
+        assert _lib.mvm_sym_distance_plan(_lib.plan_layout(J, K)) is None
+    # non-RBF base kernels: group layouts even for K = 1, no tensor-core kernel, fewer right-hand-side widths
+    rbf, mat = _lib.plan_layout(20, 1), _lib.plan_layout(20, 1, _lib.BASE_MATERN15)
+    assert (rbf.base, rbf.KP, rbf.G, rbf.CP) == (0, 1, 20, 20)
+    assert mat.base == 1 and mat.KP == 2 and mat.K == 1 and mat.G * mat.nchunks >= 20 and mat.G * mat.KP <= mat.CP
+    assert _lib.mvm_sym_supported(rbf, 11) and not _lib.mvm_sym_supported(mat, 11)
+    assert _lib.padded_rhs(mat, 11, False) == 16 and _lib.padded_rhs(rbf, 11, False) == 12
+    imq = _lib.plan_layout(3, 4, _lib.BASE_INVERSE_MQ)
+    assert imq.base == 2 and imq.KP >= 4
+    with pytest.raises(RuntimeError):
+        _lib.plan_layout(3, 4, 7)
