@@ -472,12 +472,22 @@ def main():
     ap.add_argument("--cg-tol", type=float, default=0.002)
     args = ap.parse_args()
     w = WORKLOADS[args.workload]
-    if args.mode == "mll" and args.impl == "ours":
-        return run_mll(args, w)
-    if args.impl == "reference":
-        run_reference(args, w)
-    else:
-        run_ours(args, w)
+    # stdout carries the ONE JSON line and nothing else: libraries that write to file descriptor 1 on their own (NCCL prints its
+    # version there when NCCL_DEBUG is set in the environment) are sent to stderr while the benchmark runs
+    sys.stdout.flush()
+    saved_stdout = os.dup(1)
+    os.dup2(2, 1)
+    real_stdout = os.fdopen(saved_stdout, "w")
+    sys.stdout = real_stdout
+    try:
+        if args.mode == "mll" and args.impl == "ours":
+            return run_mll(args, w)
+        if args.impl == "reference":
+            run_reference(args, w)
+        else:
+            run_ours(args, w)
+    finally:
+        real_stdout.flush()
 
 
 if __name__ == "__main__":

@@ -213,6 +213,9 @@ class RPAdditiveLazyTensor(LazyTensor):
             if self.symmetric and rdist.world_size() > 1:
                 out = ops.kmv_partitioned(self.Z1.detach(), self.c.detach(), self.J, self.K, V.detach(),
                                           packed=self._packed1, nlc=self._nlc, base=self.base)
+            elif not self.symmetric and rdist.world_size() > 1:
+                out = ops.kmv_rect_partitioned(self.Z1.detach(), self.Z2.detach(), self.c.detach(), self.J, self.K, V.detach(),
+                                               packed1=self._packed1, packed2=self._packed2, nlc=self._nlc, base=self.base)
             else:
                 Z2 = self.Z1 if self.symmetric else self.Z2
                 out = ops.kmv_raw(self.Z1.detach(), Z2.detach(), self.c.detach(), self.J, self.K, V.detach(),

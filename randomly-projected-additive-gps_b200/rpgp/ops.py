@@ -232,3 +232,17 @@ def kmv_partitioned(Z, c, J, K, V, packed=None, nlc=None, base=0):
             return rdist.all_reduce_sum(out)
     blk = kmv_raw(Z, Z, c, J, K, V, packed1=packed, packed2=packed, nlc=nlc, row_range=(part.r0, part.r1), base=base)
     return rdist.all_gather_rows(blk, part)
+
+
+RECT_MIN_ROWS_PER_RANK = 64
+
+
+def kmv_rect_partitioned(Z1, Z2, c, J, K, V, packed1=None, packed2=None, nlc=None, base=0):
+    """Rectangular K(Z1, Z2) @ V (prediction: test rows x training columns) with the ROWS of Z1 split over the ranks and one
+    all-gather of the row blocks ("test rows partitioned the same way; all-gather of n* means").  Every rank must call
+    it with the same replicated operands; small products (fewer than RECT_MIN_ROWS_PER_RANK rows per rank) stay replicated."""
+    part = rdist.partition(Z1.shape[0])
+    if part.world == 1 or Z1.shape[0] < RECT_MIN_ROWS_PER_RANK * part.world:
+        return kmv_raw(Z1, Z2, c, J, K, V, packed1=packed1, packed2=packed2, nlc=nlc, base=base)
+    blk = kmv_raw(Z1, Z2, c, J, K, V, packed1=packed1, packed2=packed2, nlc=nlc, row_range=(part.r0, part.r1), base=base)
+    return rdist.all_gather_rows(blk.contiguous(), part)
