@@ -4,6 +4,7 @@
 #include <cmath>
 #include <cstdlib>
 #include <cstring>
+#include <ctime>
 #include <vector>
 
 #include "../../include/rpgp.h"
@@ -368,6 +369,17 @@ int rpgp_kmv_host_f32(const float* X1, int64_t m, const float* X2, int64_t n, in
     } buf;
     RPGP_CUDA_OK(cudaStreamCreateWithFlags(&buf.st, cudaStreamNonBlocking));
     cudaStream_t st = buf.st;
+    // RPGP_HOST_TIMING=1: wall-clock phases of this call on stderr (adds a synchronisation after every phase)
+    static const bool timing = [] { const char* e = getenv("RPGP_HOST_TIMING"); return e && atoi(e) != 0; }();
+    auto now = [] { timespec ts; clock_gettime(CLOCK_MONOTONIC, &ts); return ts.tv_sec + 1e-9 * ts.tv_nsec; };
+    double t_prev = now();
+    auto phase = [&](const char* what) {
+        if (!timing) return;
+        cudaStreamSynchronize(st);
+        const double t_now = now();
+        fprintf(stderr, "[rpgp_kmv_host] %-28s %9.3f ms\n", what, 1e3 * (t_now - t_prev));
+        t_prev = t_now;
+    };
     float *dX1, *dX2 = nullptr, *dW, *dpre = nullptr, *dpost = nullptr, *dc, *dnlc, *dZ1, *dZ2, *dV, *dVp, *dout;
     void* dws;
     int rc;
@@ -387,6 +399,7 @@ int rpgp_kmv_host_f32(const float* X1, int64_t m, const float* X2, int64_t n, in
     if ((rc = buf.alloc((void**)&dout, (size_t)m * t * 4))) return rc;
     const size_t ws_bytes = use_sym ? rpgp_mvm_sym_workspace_bytes(n, &lay) : rpgp_mvm_workspace_bytes(m, n, &lay, tc0);
     if ((rc = buf.alloc(&dws, ws_bytes))) return rc;
+    phase("allocations");
 
     RPGP_CUDA_OK(cudaMemcpyAsync(dX1, X1, (size_t)m * d * 4, cudaMemcpyHostToDevice, st));
     if (!square) RPGP_CUDA_OK(cudaMemcpyAsync(dX2, X2, (size_t)n * d * 4, cudaMemcpyHostToDevice, st));
@@ -396,10 +409,12 @@ int rpgp_kmv_host_f32(const float* X1, int64_t m, const float* X2, int64_t n, in
     RPGP_CUDA_OK(cudaMemcpyAsync(dc, c, (size_t)J * 4, cudaMemcpyHostToDevice, st));
     RPGP_CUDA_OK(cudaMemcpyAsync(dV, V, (size_t)n * t * 4, cudaMemcpyHostToDevice, st));
 
+    phase("host -> device copies");
     if ((rc = rpgp_pack_log2c_f32(dc, &lay, dnlc, st))) return rc;
     if ((rc = rpgp_project_f32(dX1, m, d, d, dW, dpre, dpost, &lay, scale, dZ1, st))) return rc;
     if (!square && (rc = rpgp_project_f32(dX2, n, d, d, dW, dpre, dpost, &lay, scale, dZ2, st))) return rc;
     const float* z2 = square ? dZ1 : dZ2;
+    phase("projection");
     for (int t0 = 0; t0 < t; t0 += tmax) {
         const int tc = std::min(tmax, t - t0);
         const int TP = use_sym ? 16 : rpgp_padded_rhs(&lay, tc, 0);
@@ -414,8 +429,10 @@ int rpgp_kmv_host_f32(const float* X1, int64_t m, const float* X2, int64_t n, in
         if (rc) return rc;
     }
     if (square && diag_add != 0.f && (rc = launch_axpy_rows(diag_add, dV, t, m, t, dout, t, st))) return rc;
+    phase("K.V");
     RPGP_CUDA_OK(cudaMemcpyAsync(out, dout, (size_t)m * t * 4, cudaMemcpyDeviceToHost, st));
     RPGP_CUDA_OK(cudaStreamSynchronize(st));
+    phase("device -> host copy");
     return OK;
 }
 
