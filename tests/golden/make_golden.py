@@ -4,6 +4,8 @@
 
 What is executed from the reference:
   * rp.py                 imported as a module (pure torch/numpy/scipy): gen_rp (rp.py:10-32), space_equally (rp.py:220-268)
+  * postprocess_inverse_mq  the function gp_models/kernels/imq_kernel.py:8-9 (same slicing + exec; `python make_golden.py imq`
+                          writes only imq.npz): squared distance -> inverse-multiquadric kernel value
   * GAMFunction           the class body of gp_models/kernels/memory_efficient_gam_kernel.py:5-59, extracted by source
                           slicing + exec because the module header does `import gpytorch`, which is not installed here
                           (SURVEY.md §8c).  No reference source is copied into the repo: only its OUTPUTS are stored.
@@ -34,6 +36,35 @@ def load_gam_function():
     ns = {"torch": torch}
     exec(compile(src[start:end], "ref_GAMFunction", "exec"), ns)
     return ns["GAMFunction"]
+
+
+def load_postprocess_inverse_mq():
+    src = open(os.path.join(REF, "gp_models/kernels/imq_kernel.py")).read()
+    start = src.index("def postprocess_inverse_mq")
+    end = src.index("class InverseMQKernel")
+    ns = {"torch": torch}
+    exec(compile(src[start:end], "ref_postprocess_inverse_mq", "exec"), ns)
+    return ns["postprocess_inverse_mq"]
+
+
+def main_imq():
+    """InverseMQKernel.forward (imq_kernel.py:17-22): inputs divided by the lengthscale, squared distance, the reference's own
+    post-processing function; the squared distance (gpytorch covar_dist in the reference) is formed with torch.cdist here."""
+    post = load_postprocess_inverse_mq()
+    out = {}
+    sq = torch.linspace(0, 50, 101, dtype=torch.double)
+    out["grid_sq"] = sq.numpy().copy()
+    out["grid_k"] = post(sq.clone()).numpy()
+    for idx, (n, m, d) in enumerate([(9, 7, 1), (16, 12, 3), (5, 11, 6)]):
+        g = torch.Generator().manual_seed(300 + idx)
+        x1 = torch.randn(n, d, generator=g, dtype=torch.double) * 2
+        x2 = torch.randn(m, d, generator=g, dtype=torch.double) * 2
+        ls = torch.rand(1, d, generator=g, dtype=torch.double) + 0.5
+        dist = torch.cdist(x1 / ls, x2 / ls) ** 2
+        out["c%d_x1" % idx], out["c%d_x2" % idx], out["c%d_ls" % idx] = x1.numpy(), x2.numpy(), ls.numpy()
+        out["c%d_K" % idx] = post(dist.clone()).numpy()
+    np.savez(os.path.join(OUT, "imq.npz"), **out)
+    print("wrote imq.npz")
 
 
 def main():
@@ -103,4 +134,4 @@ def main():
 
 
 if __name__ == "__main__":
-    sys.exit(main())
+    sys.exit(main_imq() if sys.argv[1:] == ["imq"] else main())

@@ -49,6 +49,21 @@ def test_forward_and_rows_match_oracle(base, m, n, J, K, t):
     assert rel(rows64, orc.additive_rbf_dense(Z1[:9], Z2, c, J, K, base=base)) < 1e-12
 
 
+def test_inverse_multiquadric_rows_match_reference_fixture():
+    """dense rows of base kernel 2 against tests/golden/imq.npz (the reference's own postprocess_inverse_mq, imq_kernel.py:8-9)"""
+    import os
+    g = np.load(os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "imq.npz"))
+    for idx in range(3):
+        x1, x2, ls = g["c%d_x1" % idx], g["c%d_x2" % idx], g["c%d_ls" % idx]
+        dd = x1.shape[1]
+        z1, z2 = torch.from_numpy(x1 / ls).to(DEV), torch.from_numpy(x2 / ls).to(DEV)
+        one = torch.ones(1, dtype=torch.float64, device=DEV)
+        got64 = ops.kernel_rows_raw(z1, z2, one, 1, dd, 2).cpu().numpy()
+        assert rel(got64, g["c%d_K" % idx]) < 1e-12
+        got32 = ops.kernel_rows_raw(z1.float(), z2.float(), one.float(), 1, dd, 2).cpu().numpy()
+        assert rel(got32, g["c%d_K" % idx]) < 2e-6
+
+
 @pytest.mark.parametrize("base", [1, 2])
 @pytest.mark.parametrize("n,J,K,t", [(500, 20, 1, 11), (300, 6, 4, 3), (260, 1, 20, 16)])
 def test_quadratic_form_gradients_match_oracle(base, n, J, K, t):

@@ -160,3 +160,15 @@ def test_exact_mll_gradients_against_finite_differences():
     assert abs((nmll(Z, cp, noise, 0.1) - nmll(Z, cm, noise, 0.1)) / (2 * eps) - dc[1]) < 1e-6
     assert abs((nmll(Z, c, noise + eps, 0.1) - nmll(Z, c, noise - eps, 0.1)) / (2 * eps) - dnoise) < 1e-6
     assert abs((nmll(Z, c, noise, 0.1 + eps) - nmll(Z, c, noise, 0.1 - eps)) / (2 * eps) - dmean) < 1e-6
+
+
+def test_inverse_multiquadric_matches_reference_postprocess_function():
+    """fixtures from the reference's own `postprocess_inverse_mq` (imq_kernel.py:8-9) applied the way InverseMQKernel.forward
+    does (:17-22): pins base kernel 2 of the oracle (and through it of the CUDA kernels, tests/test_base_kernels_gpu.py)"""
+    g = np.load(os.path.join(GOLD, "imq.npz"))
+    np.testing.assert_allclose(orc.base_f(2, g["grid_sq"]), g["grid_k"], rtol=1e-14)
+    for idx in range(3):
+        x1, x2, ls = g["c%d_x1" % idx], g["c%d_x2" % idx], g["c%d_ls" % idx]
+        d = x1.shape[1]
+        K = orc.additive_rbf_dense(x1 / ls, x2 / ls, [1.0], 1, d, base=2)       # one group of d coordinates
+        np.testing.assert_allclose(K, g["c%d_K" % idx], rtol=1e-12)
