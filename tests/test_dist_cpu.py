@@ -69,6 +69,48 @@ def test_row_partition_allgather_and_cg_world2(tmp_path):
     np.testing.assert_allclose(np.load(out), torch.linalg.solve(K, rhs).numpy(), atol=1e-7)
 
 
+def _rect_worker(rank, world, port, m, n):
+    """the row-partitioned rectangular product (prediction: test rows x training columns) with the fused kernel replaced by an
+    explicit matrix: every rank multiplies only its block of test rows, one all-gather rebuilds the product"""
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    try:
+        from rpgp import lazy, ops
+        g = torch.Generator().manual_seed(1)
+        Kx = torch.randn(m, n, dtype=torch.float64, generator=g)
+        V = torch.randn(n, 2, dtype=torch.float64, generator=g)
+        calls = []
+
+        def fake_kmv_raw(Z1, Z2, c, J, K, V_, packed1=None, packed2=None, nlc=None, row_range=None, base=0):
+            calls.append(row_range)
+            r0, r1 = row_range if row_range is not None else (0, Z1.shape[0])
+            return Kx[r0:r1] @ V_
+
+        real = ops.kmv_raw
+        ops.kmv_raw = fake_kmv_raw
+        try:
+            Z1, Z2 = torch.zeros(m, 3, dtype=torch.float64), torch.zeros(n, 3, dtype=torch.float64)
+            out = ops.kmv_rect_partitioned(Z1, Z2, torch.ones(3, dtype=torch.float64), 3, 1, V)
+            assert torch.allclose(out, Kx @ V, atol=1e-12) and out.shape == (m, 2)
+            part = rdist.partition(m)
+            assert calls == [(part.r0, part.r1)] and part.r1 - part.r0 < m
+            # the operator takes that route for rectangular products when a process group exists
+            op = lazy.RPAdditiveLazyTensor(Z1, Z2, torch.ones(3, dtype=torch.float64), 3, 1)
+            assert torch.allclose(op._matmul(V), Kx @ V, atol=1e-12) and calls[-1] == (part.r0, part.r1)
+            # too few rows per rank: replicated
+            small = ops.kmv_rect_partitioned(Z1[:10], Z2, torch.ones(3, dtype=torch.float64), 3, 1, V)
+            assert calls[-1] is None and torch.allclose(small, Kx[:10] @ V, atol=1e-12)
+        finally:
+            ops.kmv_raw = real
+    finally:
+        dist.destroy_process_group()
+
+
+def test_rectangular_product_row_partition_world2():
+    mp.spawn(_rect_worker, args=(2, _free_port(), 301, 77), nprocs=2, join=True)      # 151 + 150 test rows
+
+
 def test_partition_arithmetic():
     p = rdist.Partition(10, 4, 3)
     assert (p.block, p.r0, p.r1) == (3, 9, 10)
