@@ -79,7 +79,8 @@ def test_sym_unsupported_shapes_are_reported():
 
 # ---- K > 1 with the squared distances on the tensor cores (csrc/sym_tcd.cu) ------------------------------------------------------
 @pytest.mark.parametrize("n,J,K,t", [(300, 20, 5, 11), (1000, 1, 20, 11), (1025, 10, 4, 16), (640, 2, 16, 1), (1300, 7, 8, 11),
-                                     (260, 1, 24, 2), (3000, 3, 6, 5), (129, 9, 5, 3), (4000, 20, 5, 11), (2000, 17, 7, 4)])
+                                     (260, 1, 24, 2), (3000, 3, 6, 5), (129, 9, 5, 3), (4000, 20, 5, 11), (2000, 17, 7, 4),
+                                     (50, 3, 5, 2), (128, 8, 6, 11), (33, 1, 4, 1)])
 def test_tensor_core_distances_match_oracle(n, J, K, t):
     """4 <= K <= 24: U = |z|^2 + |z'|^2 - 2 z.z' as one augmented inner product on tcgen05 (3xTF32), several groups per chunk,
     several chunks, partial last blocks; same 1e-5 bound as every other forward path."""
