@@ -85,7 +85,7 @@ def _determine_folds(split, dataset):
     size, folds = int(np.floor(n * split)), int(round(1.0 / split))
     extra = n - size * folds
     sizes = [size + 1 if i < extra else size for i in range(folds)]
-    return [0] + list(np.cumsum(sizes))
+    return [0] + [int(v) for v in np.cumsum(sizes)]
 
 
 def _access_fold(dataset, fold_starts, fold):

@@ -147,3 +147,19 @@ def test_main_writes_the_reference_csv_schema(tmp_path, monkeypatch):
         assert col in saved.columns, col
     assert (saved["dataset"] == "toy").all() and (saved["cg_tol"] == 0.01).all() and (saved["fold"] == 1).all()
     assert json.loads(saved["options"][0])["kind"] == "rp_poly"
+
+
+def test_reference_known_answers_for_the_experiment_helpers():
+    """the reference's own TestExperimentHelpers (test.py:494-529), same inputs, same expected values"""
+    df = pd.DataFrame({"index": [0, 1, 2], "0": [1, 2, 2], "target": [0, 0, 1]})
+    new_train, new_test = runner._normalize_by_train(df.iloc[:2, :], df.iloc[2:, :])
+    mean, std = 0.5, np.std([-0.5, 0.5], ddof=1)
+    assert new_train["0"].iloc[0] == (0 - mean) / std and new_test["0"].iloc[0] == (0 + mean) / std
+    assert new_test["target"].iloc[0] == 1 and new_train["target"].iloc[0] == 0        # zero-variance target: centred only
+    df4 = pd.DataFrame({"index": [0, 1, 2, 3], "0": [1, 2, 2, 4], "target": [0, 0, 1, 1]})
+    starts = runner._determine_folds(1 / 3, df4)
+    assert len(starts) == 4 and starts == [0, 2, 3, 4] and all(type(v) is int for v in starts)
+    train, test = runner._access_fold(df4, [0, 2, 3, 4], 0)
+    assert test["index"].values.tolist() == [0, 1] and train["index"].values.tolist() == [2, 3]
+    train, test = runner._access_fold(df4, [0, 2, 3, 4], 1)
+    assert test["index"].values.tolist() == [2] and train["index"].values.tolist() == [0, 1, 3]
