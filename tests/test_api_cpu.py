@@ -248,3 +248,50 @@ def test_distance_on_tensor_core_plan_and_base_layouts():
     assert imq.base == 2 and imq.KP >= 4
     with pytest.raises(RuntimeError):
         _lib.plan_layout(3, 4, 7)
+
+
+def test_random_projections_preserve_distances_like_the_reference_checks():
+    """TestRPGenerator (test.py:52-109): mean relative distortion of pairwise distances below 10 % for a 100 -> 1000 dimensional
+    projection drawn by gen_rp, for every distribution the reference tests; spherical columns have equal norms (:77)"""
+    import rp
+    torch.manual_seed(0)
+    data = torch.randn(40, 100)
+    ref = torch.cdist(data, data)
+    for dist in ("gaussian", "sphere", "bernoulli", "uniform"):
+        W = rp.gen_rp(100, 1000, dist=dist)
+        assert tuple(W.shape) == (100, 1000)
+        proj = data.matmul(W)
+        err = (ref - torch.cdist(proj, proj)).abs().mean() / ref.abs().mean()
+        assert float(err) < 0.1, (dist, float(err))
+    W = rp.gen_rp(100, 1000, dist="sphere")
+    assert abs(W[:, 0].norm().item() - W[:, 1].norm().item()) < 1e-5
+
+
+def test_strictly_additive_and_grouped_additive_kernels():
+    """TestStrictlyAdditiveKernel / TestAdditiveKernel (test.py:330-357): structure of the component kernels, `initialize`, and
+    that the grouping of the features matters -- read off the operator the kernel lowers to (no evaluation needed)"""
+    from gp_models.kernels import CustomAdditiveKernel
+    d = 5
+    kernel = StrictlyAdditiveKernel(d, RBFKernel)
+    assert isinstance(kernel.kernel, gpytorch.kernels.AdditiveKernel) and len(kernel.kernel.kernels) == d
+    assert isinstance(kernel.kernel.kernels[0].base_kernel, RBFKernel)
+    kernel.initialize([0.1, 0.1], [0.1, 0.1])
+    x = torch.randn(7, d)
+    op = kernel.forward(x, x)
+    assert isinstance(op, RPAdditiveLazyTensor) and (op.J, op.K) == (d, 1) and op.symmetric
+    np.testing.assert_allclose(op.c.detach().numpy(), np.full(d, 1.0 / d), rtol=1e-6)        # mixins normalised to sum to one
+    np.testing.assert_allclose(op.Z1.detach().numpy(), (x / 0.1).numpy(), rtol=1e-5)         # lengthscale 0.1 on every feature
+
+    k1 = CustomAdditiveKernel([[1, 2], [0, 3]], 4, RBFKernel)
+    k2 = CustomAdditiveKernel([[0, 1], [2, 3]], 4, RBFKernel)
+    assert isinstance(k1.kernel.kernels[0].base_kernel.kernels[0], RBFKernel)
+    xx = torch.tensor([[0., 1., 2., 3.], [0., 1., 4., 5.]])
+    o1, o2 = k1.forward(xx, xx), k2.forward(xx, xx)
+    assert (o1.J, o1.K) == (2, 2) and (o2.J, o2.K) == (2, 2)
+
+    def dense(o):      # the operator's definition, in torch (CPU): sum_j c_j exp(-1/2 |z_i^(j) - z_i'^(j)|^2)
+        z = o.Z1.detach().reshape(o.Z1.shape[0], o.J, o.K)
+        sq = ((z[:, None] - z[None, :]) ** 2).sum(-1)
+        return (o.c.detach() * torch.exp(-0.5 * sq)).sum(-1)
+
+    assert abs(float(dense(o1)[0, 1]) - float(dense(o2)[0, 1])) > 1e-3                       # test.py:350-357
