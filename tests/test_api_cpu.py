@@ -295,3 +295,48 @@ def test_strictly_additive_and_grouped_additive_kernels():
         return (o.c.detach() * torch.exp(-0.5 * sq)).sum(-1)
 
     assert abs(float(dense(o1)[0, 1]) - float(dense(o2)[0, 1])) > 1e-3                       # test.py:350-357
+
+
+def test_additive_models_structure_and_conversion():
+    """gp_models/models.py:23-86,110-125 on the host: kernel-type checks, groups, and the RP -> additive conversion shares the
+    component kernels / likelihood / mean and carries the projected training inputs (numerics: tests/test_model_gpu.py)"""
+    from gp_models import AdditiveExactGPModel, CustomAdditiveKernel, ProjectedAdditiveExactGPModel, convert_rp_model_to_additive_model
+    x, y = torch.randn(6, 4), torch.randn(6)
+    lik = gpytorch.likelihoods.GaussianLikelihood()
+    groups = [[1, 2], [0, 3]]
+    m = AdditiveExactGPModel(x, y, lik, CustomAdditiveKernel(groups, 4, RBFKernel))
+    assert m.get_groups() == groups
+    ms = AdditiveExactGPModel(x, y, lik, ScaleKernel(StrictlyAdditiveKernel(4, RBFKernel)))
+    assert ms.get_groups() == [[0], [1], [2], [3]]
+    for bad in (RBFKernel(), ScaleKernel(RBFKernel())):
+        with pytest.raises(ValueError):
+            AdditiveExactGPModel(x, y, lik, bad)
+        with pytest.raises(ValueError):
+            ProjectedAdditiveExactGPModel(x, y, lik, bad)
+    Ws, bs = [torch.eye(4, 2) for _ in range(3)], [torch.zeros(2) for _ in range(3)]
+    rp_kernel = PolynomialProjectionKernel(3, 2, 4, RBFKernel, Ws, bs, learn_proj=False, weighted=True)
+    rp_model = ProjectedAdditiveExactGPModel(x, y, lik, rp_kernel)
+    add_model, proj = rp_model.get_corresponding_additive_model()
+    assert isinstance(add_model, AdditiveExactGPModel) and proj is rp_kernel.projection_module
+    assert add_model.covar_module.kernel is rp_kernel.kernel and add_model.likelihood is lik and add_model.mean_module is rp_model.mean_module
+    assert add_model.get_groups() == [[0, 1], [2, 3], [4, 5]] and tuple(add_model.train_inputs[0].shape) == (6, 6)
+    np.testing.assert_allclose(add_model.train_inputs[0].numpy(), proj(x).detach().numpy())
+    wrapped = ExactGPModel(x, y, lik, ScaleKernel(rp_kernel))
+    wrapped.covar_module.outputscale = 2.5
+    add2 = convert_rp_model_to_additive_model(wrapped, return_proj=False)
+    assert isinstance(add2.covar_module, ScaleKernel) and abs(float(add2.covar_module.outputscale.detach()) - 2.5) < 1e-6
+
+
+def test_multivariate_normal_sum_and_sampling():
+    from rpgp.gp.distributions import MultivariateNormal
+    a = MultivariateNormal(torch.tensor([1.0, 2.0]), torch.tensor([[2.0, 0.5], [0.5, 1.0]]))
+    b = MultivariateNormal(torch.tensor([0.5, -1.0]), torch.eye(2))
+    s = a + b
+    np.testing.assert_allclose(s.mean.numpy(), [1.5, 1.0])
+    np.testing.assert_allclose(s.covariance_matrix.numpy(), [[3.0, 0.5], [0.5, 2.0]])
+    torch.manual_seed(0)
+    draws = a.sample(torch.Size([20000]))
+    assert tuple(draws.shape) == (20000, 2)
+    np.testing.assert_allclose(draws.mean(0).numpy(), [1.0, 2.0], atol=0.05)
+    np.testing.assert_allclose(np.cov(draws.numpy().T), [[2.0, 0.5], [0.5, 1.0]], atol=0.08)
+    assert tuple(a.sample().shape) == (2,)

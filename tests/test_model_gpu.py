@@ -429,3 +429,87 @@ def test_experiment_runner_end_to_end(tmp_path):
     import pandas as pd
     saved = pd.read_csv(out)
     assert bool(saved["fast_pred_var"][0]) and saved["dataset"][0] == "synthetic" and abs(saved["cg_tol"][0] - 0.01) < 1e-12
+
+
+@pytest.mark.parametrize("wrap", [False, True])
+def test_additive_component_posteriors(wrap):
+    """TestAdditivePredictions (test.py:384-457): per-component posteriors of an additive model -- equal for equal inputs,
+    different otherwise, their means add up to the model's predictive mean -- then at a size where the solve runs through CG on
+    the fused kernels, against the dense FP64 formula K_j* K^-1 y."""
+    from gp_models import AdditiveExactGPModel, StrictlyAdditiveKernel
+    kernel = StrictlyAdditiveKernel(2, RBFKernel)
+    if wrap:
+        kernel = ScaleKernel(kernel)
+    lik = gpytorch.likelihoods.GaussianLikelihood()
+    trainX, trainY = torch.tensor([[0., 0.]], device=DEV), torch.tensor([2.], device=DEV)
+    model = AdditiveExactGPModel(trainX, trainY, lik, kernel).to(DEV)
+    model.eval()
+    equi = model.additive_pred(torch.tensor([[1., 1.]], device=DEV))
+    diff = model.additive_pred(torch.tensor([[1., 0.]], device=DEV))
+    assert abs(float(equi[0].mean[0]) - float(equi[1].mean[0])) < 1e-7
+    assert abs(float(diff[0].mean[0]) - float(diff[1].mean[0])) > 1e-3
+    with torch.no_grad():
+        total = model(torch.tensor([[1., 0.]], device=DEV))
+    combined = diff[0] + diff[1]
+    assert abs(float(combined.mean[0]) - float(total.mean[0])) < 1e-6
+    assert float(model.additive_pred(torch.tensor([[1., 0.], [1.1, 1.2]], device=DEV), group=1).variance.min()) > 0
+
+    # n = 1500: CG on the symmetric tensor-core kernel, rectangular single-group products for the component means
+    g = torch.Generator().manual_seed(3)
+    X = torch.rand(1500, 2, generator=g).to(DEV) * 4 - 2
+    y = (torch.sin(X[:, 0]) + torch.cos(2 * X[:, 1]) + 0.1 * torch.randn(1500, generator=g).to(DEV))
+    Xt = torch.rand(64, 2, generator=g).to(DEV) * 4 - 2
+    kernel = StrictlyAdditiveKernel(2, RBFKernel)
+    kernel.initialize([1.0, 1.0], [0.7, 0.7])
+    if wrap:
+        kernel = ScaleKernel(kernel)
+        kernel.outputscale = 1.7
+    model = AdditiveExactGPModel(X, y, gpytorch.likelihoods.GaussianLikelihood(), kernel).to(DEV)
+    model.eval()
+    with settings.eval_cg_tolerance(1e-6), settings.max_cg_iterations(4000), warnings.catch_warnings():
+        warnings.simplefilter("ignore")
+        preds = model.additive_pred(Xt)
+        with torch.no_grad():
+            total = model(Xt).mean
+        var0 = preds[0].variance.cpu().numpy()
+    assert len(preds) == 2
+    summed = (preds[0] + preds[1]).mean
+    assert rel(summed.cpu().numpy(), total.cpu().numpy()) < 1e-4
+    # dense FP64 reference of component 0
+    ls = 0.7
+    s = 1.7 if wrap else 1.0
+    Xd, Xtd, yd = X.cpu().double().numpy(), Xt.cpu().double().numpy(), y.cpu().double().numpy()
+    k = lambda a, b: 0.5 * s * np.exp(-0.5 * ((a[:, None] - b[None, :]) / ls) ** 2)
+    Kfull = k(Xd[:, 0], Xd[:, 0]) + k(Xd[:, 1], Xd[:, 1]) + float(model.likelihood.noise) * np.eye(1500)
+    alpha = np.linalg.solve(Kfull, yd)
+    ref_mean0 = k(Xtd[:, 0], Xd[:, 0]) @ alpha
+    assert rel(preds[0].mean.cpu().numpy(), ref_mean0) < 2e-3, rel(preds[0].mean.cpu().numpy(), ref_mean0)
+    c0 = k(Xtd[:, 0], Xd[:, 0])
+    ref_var0 = np.diag(k(Xtd[:, 0], Xtd[:, 0]) - c0 @ np.linalg.solve(Kfull, c0.T))
+    assert rel(var0, ref_var0) < 5e-3, rel(var0, ref_var0)
+    assert tuple(preds[1].sample(torch.Size([3])).shape) == (3, 64)
+
+
+def test_rp_model_equals_its_additive_conversion():
+    """test.py:359-380: after one optimiser step the additive model over the projected inputs predicts what the RP model predicts"""
+    from gp_models import convert_rp_model_to_additive_model
+    g = torch.Generator().manual_seed(8)
+    X, y = torch.randn(300, 2, generator=g).to(DEV), torch.randn(300, generator=g).to(DEV)
+    Xt = torch.randn(40, 2, generator=g).to(DEV)
+    Ws, bs = [torch.eye(2, 2) for _ in range(3)], [torch.zeros(2) for _ in range(3)]
+    kernel = PolynomialProjectionKernel(3, 2, 2, RBFKernel, Ws, bs, learn_proj=False, weighted=True)
+    lik = gpytorch.likelihoods.GaussianLikelihood()
+    model = ExactGPModel(X, y, lik, kernel).to(DEV)
+    mll = gpytorch.mlls.ExactMarginalLogLikelihood(lik, model)
+    opt = torch.optim.Adam(model.parameters(), lr=0.01)
+    opt.zero_grad()
+    loss = -mll(model(X), y)
+    loss.backward()
+    opt.step()
+    add_model, projection = convert_rp_model_to_additive_model(model, True)
+    add_model.eval()
+    model.eval()
+    with torch.no_grad():
+        got = add_model(projection(Xt)).mean
+        want = model(Xt).mean
+    assert rel(got.cpu().numpy(), want.cpu().numpy()) < 1e-5
