@@ -480,7 +480,7 @@ def test_additive_component_posteriors(wrap):
     s = 1.7 if wrap else 1.0
     Xd, Xtd, yd = X.cpu().double().numpy(), Xt.cpu().double().numpy(), y.cpu().double().numpy()
     k = lambda a, b: 0.5 * s * np.exp(-0.5 * ((a[:, None] - b[None, :]) / ls) ** 2)
-    Kfull = k(Xd[:, 0], Xd[:, 0]) + k(Xd[:, 1], Xd[:, 1]) + float(model.likelihood.noise) * np.eye(1500)
+    Kfull = k(Xd[:, 0], Xd[:, 0]) + k(Xd[:, 1], Xd[:, 1]) + float(model.likelihood.noise.detach()) * np.eye(1500)
     alpha = np.linalg.solve(Kfull, yd)
     ref_mean0 = k(Xtd[:, 0], Xd[:, 0]) @ alpha
     assert rel(preds[0].mean.cpu().numpy(), ref_mean0) < 2e-3, rel(preds[0].mean.cpu().numpy(), ref_mean0)
