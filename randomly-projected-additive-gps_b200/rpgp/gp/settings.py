@@ -3,7 +3,6 @@ gp_experiment_runner.py:324-332 and synthetic_test_script.py:122-123.
 
     with settings.cg_tolerance(0.002), settings.eval_cg_tolerance(0.001), settings.max_cg_iterations(10_000): ...
 """
-import torch
 
 
 class _Value:

@@ -7,14 +7,12 @@ it exposes the methods the CG / Lanczos MLL and the prediction strategy call on 
 routes all arithmetic to the fused sm_100a kernels (rpgp/ops.py).  `AddedDiagLazyTensor` is K + sigma_n^2 I (what the
 likelihood adds), `DenseLazyTensor` wraps an explicit matrix (predictive covariances).
 """
-import math
-
 import torch
 
 from . import dist as rdist
 from . import ops
 from .solver.linear_cg import linear_cg
-from .solver.preconditioner import PivCholPreconditioner, pivoted_cholesky, slq_logdet
+from .solver.preconditioner import PivCholPreconditioner, pivoted_cholesky
 
 
 def _settings():

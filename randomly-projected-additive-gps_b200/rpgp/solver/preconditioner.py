@@ -4,8 +4,6 @@ gp_experiment_runner.py:324-332).
 
 The operator only has to serve `diag()` and single rows `rows([p])`.
 """
-import math
-
 import torch
 
 

@@ -2,7 +2,6 @@
 the direct-difference kernel (RPGP_SYM_TCD=0, separate process).  Usage: python tools/tcd_check.py [acc|time] ..."""
 import os
 import sys
-import time
 
 import numpy as np
 import torch
