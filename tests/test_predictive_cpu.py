@@ -81,3 +81,31 @@ def test_joint_log_prob_through_the_lazy_covariance():
     want = torch.distributions.MultivariateNormal(mean, ref + noise * torch.eye(m, dtype=K.dtype)).log_prob(ys)
     np.testing.assert_allclose(float(dist.log_prob(ys)), float(want), rtol=1e-9)
     np.testing.assert_allclose(dist.variance.numpy(), (ref.diagonal() + noise).numpy(), rtol=1e-9)
+
+
+def test_joint_log_prob_through_cg_on_the_lazy_covariance():
+    """large n*: the joint test log-probability runs CG + stochastic Lanczos quadrature (with the pivoted-Cholesky preconditioner,
+    which fetches rows and the diagonal of the LAZY predictive covariance) instead of a dense Cholesky factor"""
+    from rpgp.gp.distributions import MultivariateNormal
+    K, Ks, Kss, noise = _problem(n=70, m=60, seed=5)
+    n, m = K.shape[0], Ks.shape[0]
+    ref = Kss - Ks @ torch.linalg.solve(K + noise * torch.eye(n, dtype=K.dtype), Ks.t())
+    train = lazy.AddedDiagLazyTensor(lazy.DenseLazyTensor(K), torch.tensor(noise, dtype=K.dtype))
+    cov = lazy.PredictiveCovarLazyTensor(lazy.DenseLazyTensor(Kss), lazy.DenseLazyTensor(Ks), train)
+    ys = torch.randn(m, dtype=K.dtype, generator=torch.Generator().manual_seed(6))
+    full = ref + noise * torch.eye(m, dtype=K.dtype)
+    want_iq = float(ys @ torch.linalg.solve(full, ys))
+    want_ld = float(torch.logdet(full))
+    probes = torch.randn(m, 200, dtype=K.dtype, generator=torch.Generator().manual_seed(7))
+    for precond_size in (0, 10):
+        op = cov.add_diag(torch.tensor(noise, dtype=K.dtype))
+        with settings.max_cholesky_size(0), settings.min_preconditioning_size(1), settings.max_preconditioner_size(precond_size), \
+                settings.cg_tolerance(1e-10), settings.eval_cg_tolerance(1e-12), settings.num_trace_samples(200), \
+                settings.deterministic_probes(probes):      # (the inner solves with K + sigma^2 I are CG too: nested)
+            assert not op._use_cholesky()
+            iq, ld = op.inv_quad_logdet(inv_quad_rhs=ys.unsqueeze(-1), logdet=True)
+            assert (op._preconditioner() is not None) == (precond_size > 0)
+        np.testing.assert_allclose(float(iq), want_iq, rtol=1e-7)
+        assert abs(float(ld) - want_ld) < 0.05 * abs(want_ld) + 0.5, (float(ld), want_ld)      # SLQ: 200 probes
+        dist = MultivariateNormal(torch.zeros(m, dtype=K.dtype), op)
+        assert np.isfinite(float(dist.variance.min()))
