@@ -60,3 +60,17 @@ def test_operators_of_different_base_kernels_do_not_merge():
         lazy.RPAdditiveLazyTensor.product([one, one])
     op = gk.InverseMQKernel().forward(Z, Z)
     assert op.base == 2
+
+
+@pytest.mark.parametrize("base", [0, 1, 2])
+def test_operator_diagonals_need_no_kernel_launch(base):
+    """diag of K(Z, Z) is sum_j c_j for every base kernel (k(0) = 1); diag of a square K(Z1, Z2) is formed in torch"""
+    g = torch.Generator().manual_seed(base)
+    Z1, Z2 = torch.randn(9, 6, generator=g, dtype=torch.float64), torch.randn(9, 6, generator=g, dtype=torch.float64)
+    c = torch.rand(3, generator=g, dtype=torch.float64) + 0.1
+    sym = lazy.RPAdditiveLazyTensor(Z1, None, c, 3, 2, base=base)
+    np.testing.assert_allclose(sym.diag().numpy(), np.full(9, float(c.sum())), rtol=1e-12)
+    rect = lazy.RPAdditiveLazyTensor(Z1, Z2, c, 3, 2, base=base)
+    want = np.diag(orc.additive_rbf_dense(Z1.numpy(), Z2.numpy(), c.numpy(), 3, 2, base=base))
+    np.testing.assert_allclose(rect.diag().numpy(), want, rtol=1e-12)
+    assert rect.shape == (9, 9) and rect._transpose_nonbatch().Z1 is Z2 and rect._rebuild(*rect.representation()).base == base
