@@ -81,15 +81,28 @@ constexpr int BASE_RBF = 0, BASE_MATERN15 = 1, BASE_IMQ = 2;
 constexpr float MATERN_C = 4.1588830833596715f;      // 3 * 2 ln2: (sqrt3 r)^2 = MATERN_C * u
 constexpr float TWO_LN2_F = 1.3862943611198906f;
 
+// one MUFU each (sqrtf / rsqrtf expand to range checks and Newton steps; the .approx forms are accurate to ~2^-23)
+__device__ __forceinline__ float sqrt_approx_ftz(float x) {
+    float y;
+    asm("sqrt.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
+    return y;
+}
+__device__ __forceinline__ float rsqrt_approx_ftz(float x) {
+    float y;
+    asm("rsqrt.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
+    return y;
+}
+
 template <int BASE>
 __device__ __forceinline__ float base_value(float u, float nl, float cw) {
     if constexpr (BASE == BASE_RBF) {
         return ex2_ftz(-(u + nl));
     } else if constexpr (BASE == BASE_MATERN15) {
-        const float q = sqrtf(fmaxf(MATERN_C * u, 0.f));
-        return cw * fmaf(q, ex2_ftz(-q * LOG2E_F), ex2_ftz(-q * LOG2E_F));
+        const float q = sqrt_approx_ftz(fmaxf(MATERN_C * u, 0.f));
+        const float e = ex2_ftz(-q * LOG2E_F);
+        return cw * fmaf(q, e, e);
     } else {
-        return cw * rsqrtf(fmaf(TWO_LN2_F, u, 1.f));
+        return cw * rsqrt_approx_ftz(fmaf(TWO_LN2_F, u, 1.f));
     }
 }
 
@@ -99,12 +112,12 @@ __device__ __forceinline__ void base_value_slope(float u, float nl, float cw, fl
         k = ex2_ftz(-(u + nl));
         kz = k;
     } else if constexpr (BASE == BASE_MATERN15) {
-        const float q = sqrtf(fmaxf(MATERN_C * u, 0.f));
+        const float q = sqrt_approx_ftz(fmaxf(MATERN_C * u, 0.f));
         const float e = cw * ex2_ftz(-q * LOG2E_F);
         k = fmaf(q, e, e);
         kz = 3.f * e;                      // -dk/du = c (MATERN_C / 2) e^-q ; / ln2 = 3 c e^-q
     } else {
-        const float rs = rsqrtf(fmaf(TWO_LN2_F, u, 1.f));
+        const float rs = rsqrt_approx_ftz(fmaf(TWO_LN2_F, u, 1.f));
         k = cw * rs;
         kz = k * rs * rs;                  // -dk/du = c ln2 rs^3
     }
