@@ -169,7 +169,7 @@ def create_strictly_additive_kernel(d, weighted=False, kernel_type="RBF", init_l
                                     init_mixin_range=(1.0, 1.0), ski=False, ski_options=None, X=None, keops=False,
                                     memory_efficient=False):
     _no_ski(ski)
-    if memory_efficient:
+    if kernel_type == "RBF" and memory_efficient:
         kernel = MemoryEfficientGamKernel(ard_num_dims=d)
         kernel.initialize(lengthscale=_sample_from_range(d, init_lengthscale_range))
         return kernel

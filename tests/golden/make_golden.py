@@ -67,6 +67,25 @@ def main_imq():
     print("wrote imq.npz")
 
 
+def main_synth():
+    """the target functions of synthetic_test_script.py:20-75 (source slicing + exec: the module imports gpytorch / matplotlib and
+    runs an experiment at import time); `python make_golden.py synth` writes only synthetic_targets.npz"""
+    src = open(os.path.join(REF, "synthetic_test_script.py")).read()
+    start = src.index("def unimodal_d_dim")
+    end = src.index("def benchmark_on_n_pts")
+    from math import pi, sqrt
+    ns = {"torch": torch, "pi": pi, "sqrt": sqrt, "np": np}
+    exec(compile(src[start:end], "ref_synthetic_targets", "exec"), ns)
+    g = torch.Generator().manual_seed(77)
+    x = torch.rand(9, 6, generator=g) * 4 - 2
+    out = {"x": x.numpy()}
+    for name in ["unimodal_d_dim", "bimodal_d_dim", "multimodal_d_dim", "leading_dim", "one_dim", "half_relevant", "nonseparable",
+                 "additive", "non_additive"]:
+        out[name] = ns[name](x.clone()).numpy()
+    np.savez(os.path.join(OUT, "synthetic_targets.npz"), **out)
+    print("wrote synthetic_targets.npz")
+
+
 def main():
     rp = load_rp()
     GAM = load_gam_function()
@@ -134,4 +153,4 @@ def main():
 
 
 if __name__ == "__main__":
-    sys.exit(main_imq() if sys.argv[1:] == ["imq"] else main())
+    sys.exit(main_imq() if sys.argv[1:] == ["imq"] else main_synth() if sys.argv[1:] == ["synth"] else main())

@@ -513,3 +513,20 @@ def test_rp_model_equals_its_additive_conversion():
         got = add_model(projection(Xt)).mean
         want = model(Xt).mean
     assert rel(got.cpu().numpy(), want.cpu().numpy()) < 1e-5
+
+
+def test_synthetic_benchmark_point():
+    """one point of a synthetic_test_script.py learning curve (BASELINE configs[0] at reduced size): the additive target in 6
+    dimensions, 640 training points, the GAM model, trained with Adam through CG on the fused kernels; hold-out RMSE well below 1
+    (the targets are standardised)"""
+    import synthetic_test_script as sts
+    torch.manual_seed(4)
+    np.random.seed(4)
+    ho_x = torch.rand(1000, 6) * 4 - 2
+    ho_y = sts.additive(ho_x)
+    with warnings.catch_warnings():
+        warnings.simplefilter("ignore")
+        mses, models, mlls = sts.benchmark_on_n_pts(640, sts.create_gam_model, sts.additive, ho_x, ho_y, repeats=1, max_iter=30,
+                                                    return_model=True, device="cuda:0")
+    assert len(mses) == 1 and len(models) == 1 and np.isfinite(mses[0])
+    assert np.sqrt(mses[0]) < 0.3, mses
