@@ -160,6 +160,30 @@ int rpgp_kmv_host_f32(const float* X1, int64_t m, const float* X2, int64_t n, in
                       const float* pre_inv, const float* post_inv, const float* c, const float* V, int t,
                       float diag_add, float* out, int device);
 
+/* the same path as a persistent PLAN (what a binding inside the reference's kernel classes keeps per model): device buffers for
+ * X, W, the scales, c, the packed Z^, V, the product and the workspace are allocated ONCE; every call only copies and computes.
+ *   rpgp_plan_create        n x d inputs, J x K projections, at most tmax right-hand sides; `stream` = the caller's cudaStream_t
+ *                           (e.g. torch's current stream, so that a collective on the product orders naturally) or NULL for a
+ *                           stream owned by the plan.
+ *   rpgp_plan_set_operator  H2D of X, W, pre_inv / post_inv (may be NULL), c and the projection -> packed Z^; once per MLL step
+ *                           (scaled_projection_kernel.py:21-37 recomputes it per Kernel.forward; the CG iterations reuse it).
+ *   rpgp_plan_kmv_begin     H2D of V (n x t) and the symmetric product K(X,X) V restricted to the unique block pairs of the 128-row
+ *                           blocks [row_block_begin, row_block_end) -- the full range [0, ceil(n/128)) is the whole product, a
+ *                           sub-range is one rank's share and rpgp_plan_device_out() (n x t floats, row stride t) must then be
+ *                           summed over the ranks (NCCL all-reduce on `stream`) before rpgp_plan_kmv_end.  Asynchronous.
+ *                           n < 1024 or a layout outside rpgp_mvm_sym_supported: rows [128*begin, 128*end) by the SIMT forward
+ *                           kernel, the other rows of the product are zero (same contract: sum over ranks = K V).
+ *   rpgp_plan_kmv_end       product += diag_add * V; D2H of rows [row_begin, row_end) into `out` ((row_end-row_begin) x t); synchronises.
+ * Host pointers may be pageable or pinned (pinned makes the copies asynchronous and full-speed). */
+typedef struct rpgp_plan rpgp_plan;
+int rpgp_plan_create(int64_t n, int d, int J, int K, int tmax, int device, void* stream, rpgp_plan** out);
+int rpgp_plan_destroy(rpgp_plan* plan);
+int rpgp_plan_set_operator(rpgp_plan* plan, const float* X, const float* W, const float* pre_inv, const float* post_inv,
+                           const float* c);
+int rpgp_plan_kmv_begin(rpgp_plan* plan, const float* V, int t, int row_block_begin, int row_block_end);
+void* rpgp_plan_device_out(rpgp_plan* plan);
+int rpgp_plan_kmv_end(rpgp_plan* plan, float diag_add, float* out, int64_t row_begin, int64_t row_end);
+
 /* issue-rate microbenchmarks (roofline denominators): out[4*i..] = {fp32 lane-ops/clk/SM, mufu/clk/SM, ms, MHz} */
 int rpgp_measure_peaks(double* out, int max_ops, const char** names);
 

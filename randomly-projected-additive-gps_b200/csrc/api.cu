@@ -436,4 +436,146 @@ int rpgp_kmv_host_f32(const float* X1, int64_t m, const float* X2, int64_t n, in
     return OK;
 }
 
+
+// ---- the host-buffer path as a persistent plan ------------------------------------------------------------------------------
+struct rpgp_plan {
+    long long n;
+    int d, J, K, tmax, device;
+    rpgp_layout lay;
+    bool use_sym, own_stream, has_operator;
+    cudaStream_t st;
+    float *dX, *dW, *dpre, *dpost, *dc, *dnlc, *dZ, *dV, *dVp, *dout;
+    void* dws;
+    size_t ws_bytes;
+    int t_last;
+};
+
+static void plan_free(rpgp_plan* p) {
+    if (!p) return;
+    cudaSetDevice(p->device);
+    for (void* q : {(void*)p->dX, (void*)p->dW, (void*)p->dpre, (void*)p->dpost, (void*)p->dc, (void*)p->dnlc, (void*)p->dZ, (void*)p->dV,
+                    (void*)p->dVp, (void*)p->dout, p->dws})
+        if (q) cudaFree(q);
+    if (p->own_stream && p->st) cudaStreamDestroy(p->st);
+    delete p;
+}
+
+int rpgp_plan_create(int64_t n, int d, int J, int K, int tmax, int device, void* stream, rpgp_plan** out) {
+    RPGP_REQUIRE(out != nullptr, "plan_create: out is NULL");
+    *out = nullptr;
+    RPGP_REQUIRE(n >= 1 && d >= 1 && J >= 1 && K >= 1 && tmax >= 1, "plan_create: bad shape n=%lld d=%d J=%d K=%d tmax=%d", (long long)n, d, J, K, tmax);
+    RPGP_CUDA_OK(cudaSetDevice(device));
+    rpgp_plan* p = new rpgp_plan();
+    std::memset(p, 0, sizeof(*p));
+    p->n = n; p->d = d; p->J = J; p->K = K; p->tmax = tmax; p->device = device;
+    if (int rc = rpgp_plan_layout(J, K, &p->lay)) { delete p; return rc; }
+    p->use_sym = n >= 1024 && rpgp_mvm_sym_supported(&p->lay, std::min(tmax, 16));
+    p->own_stream = (stream == nullptr);
+    p->st = (cudaStream_t)stream;
+    auto fail = [&](int rc) { plan_free(p); return rc; };
+    if (p->own_stream) {
+        cudaError_t e = cudaStreamCreateWithFlags(&p->st, cudaStreamNonBlocking);
+        if (e != cudaSuccess) return fail(cuda_fail(e, "cudaStreamCreateWithFlags"));
+    }
+    const int JK = J * K;
+    const int tper = p->use_sym ? 16 : rpgp_max_rhs(&p->lay, 0);
+    const int TPmax = p->use_sym ? 16 : rpgp_padded_rhs(&p->lay, std::min(tmax, tper), 0);
+    p->ws_bytes = p->use_sym ? rpgp_mvm_sym_workspace_bytes(n, &p->lay) : rpgp_mvm_workspace_bytes(n, n, &p->lay, std::min(tmax, tper));
+    struct { void** ptr; size_t bytes; } allocs[] = {
+        {(void**)&p->dX, (size_t)n * d * 4}, {(void**)&p->dW, (size_t)JK * d * 4}, {(void**)&p->dpre, (size_t)d * 4},
+        {(void**)&p->dpost, (size_t)JK * 4}, {(void**)&p->dc, (size_t)J * 4}, {(void**)&p->dnlc, (size_t)p->lay.nchunks * p->lay.G * 4},
+        {(void**)&p->dZ, (size_t)p->lay.nchunks * n * p->lay.CP * 4}, {(void**)&p->dV, (size_t)n * tmax * 4},
+        {(void**)&p->dVp, (size_t)n * TPmax * 4}, {(void**)&p->dout, (size_t)n * tmax * 4}, {&p->dws, p->ws_bytes}};
+    for (auto& a : allocs) {
+        cudaError_t e = cudaMalloc(a.ptr, a.bytes ? a.bytes : 16);
+        if (e != cudaSuccess) return fail(cuda_fail(e, "cudaMalloc (rpgp_plan_create)"));
+    }
+    *out = p;
+    return OK;
+}
+
+int rpgp_plan_destroy(rpgp_plan* p) {
+    plan_free(p);
+    return OK;
+}
+
+int rpgp_plan_set_operator(rpgp_plan* p, const float* X, const float* W, const float* pre_inv, const float* post_inv, const float* c) {
+    RPGP_REQUIRE(p && X && W && c, "plan_set_operator: NULL pointer");
+    RPGP_CUDA_OK(cudaSetDevice(p->device));
+    cudaStream_t st = p->st;
+    const int JK = p->J * p->K;
+    RPGP_CUDA_OK(cudaMemcpyAsync(p->dX, X, (size_t)p->n * p->d * 4, cudaMemcpyHostToDevice, st));
+    RPGP_CUDA_OK(cudaMemcpyAsync(p->dW, W, (size_t)JK * p->d * 4, cudaMemcpyHostToDevice, st));
+    if (pre_inv) RPGP_CUDA_OK(cudaMemcpyAsync(p->dpre, pre_inv, (size_t)p->d * 4, cudaMemcpyHostToDevice, st));
+    if (post_inv) RPGP_CUDA_OK(cudaMemcpyAsync(p->dpost, post_inv, (size_t)JK * 4, cudaMemcpyHostToDevice, st));
+    RPGP_CUDA_OK(cudaMemcpyAsync(p->dc, c, (size_t)p->J * 4, cudaMemcpyHostToDevice, st));
+    if (int rc = rpgp_pack_log2c_f32(p->dc, &p->lay, p->dnlc, st)) return rc;
+    if (int rc = rpgp_project_f32(p->dX, p->n, p->d, p->d, p->dW, pre_inv ? p->dpre : nullptr, post_inv ? p->dpost : nullptr, &p->lay,
+                                  (float)COORD_SCALE_D, p->dZ, st))
+        return rc;
+    p->has_operator = true;
+    return OK;
+}
+
+int rpgp_plan_kmv_begin(rpgp_plan* p, const float* V, int t, int rb_begin, int rb_end) {
+    RPGP_REQUIRE(p && V, "plan_kmv_begin: NULL pointer");
+    RPGP_REQUIRE(p->has_operator, "plan_kmv_begin: rpgp_plan_set_operator has not been called");
+    RPGP_REQUIRE(t >= 1 && t <= p->tmax, "plan_kmv_begin: t=%d outside [1, tmax=%d]", t, p->tmax);
+    const long long n = p->n;
+    const int nblocks = (int)((n + 127) / 128);
+    RPGP_REQUIRE(0 <= rb_begin && rb_begin <= rb_end && rb_end <= nblocks, "plan_kmv_begin: row block range [%d, %d) outside [0, %d]", rb_begin,
+                 rb_end, nblocks);
+    RPGP_CUDA_OK(cudaSetDevice(p->device));
+    cudaStream_t st = p->st;
+    RPGP_CUDA_OK(cudaMemcpyAsync(p->dV, V, (size_t)n * t * 4, cudaMemcpyHostToDevice, st));
+    const int tper = p->use_sym ? 16 : rpgp_max_rhs(&p->lay, 0);
+    const long long r0 = std::min<long long>(n, 128LL * rb_begin), r1 = std::min<long long>(n, 128LL * rb_end);
+    if (!p->use_sym && (r0 > 0 || r1 < n)) RPGP_CUDA_OK(cudaMemsetAsync(p->dout, 0, (size_t)n * t * 4, st));
+    for (int t0 = 0; t0 < t; t0 += tper) {
+        const int tc = std::min(tper, t - t0);
+        const int TP = p->use_sym ? 16 : rpgp_padded_rhs(&p->lay, tc, 0);
+        RPGP_CUDA_OK(cudaMemsetAsync(p->dVp, 0, (size_t)n * TP * 4, st));
+        RPGP_CUDA_OK(cudaMemcpy2DAsync(p->dVp, (size_t)TP * 4, p->dV + t0, (size_t)t * 4, (size_t)tc * 4, (size_t)n, cudaMemcpyDeviceToDevice, st));
+        int rc;
+        if (p->use_sym)
+            rc = rpgp_mvm_sym_f32(p->dZ, n, &p->lay, p->dnlc, p->dVp, tc, p->dout + t0, t, rb_begin, rb_end, p->dws, p->ws_bytes, st);
+        else if (r1 > r0) {
+            const size_t need = rpgp_mvm_workspace_bytes(r1 - r0, n, &p->lay, tc);      // the split plan depends on the block height
+            if (need > p->ws_bytes) {
+                RPGP_CUDA_OK(cudaStreamSynchronize(st));
+                if (p->dws) cudaFree(p->dws);
+                p->dws = nullptr;
+                p->ws_bytes = 0;
+                RPGP_CUDA_OK(cudaMalloc(&p->dws, need));
+                p->ws_bytes = need;
+            }
+            rc = rpgp_mvm_fwd_f32(p->dZ + r0 * p->lay.CP, r1 - r0, n * p->lay.CP, p->dZ, n, n * p->lay.CP, &p->lay, p->dnlc, p->dVp, tc,
+                                  p->dout + r0 * t + t0, t, p->dws, p->ws_bytes, st);
+        } else
+            rc = OK;
+        if (rc) return rc;
+    }
+    p->t_last = t;
+    return OK;
+}
+
+void* rpgp_plan_device_out(rpgp_plan* p) { return p ? (void*)p->dout : nullptr; }
+
+int rpgp_plan_kmv_end(rpgp_plan* p, float diag_add, float* out, int64_t row_begin, int64_t row_end) {
+    RPGP_REQUIRE(p && out, "plan_kmv_end: NULL pointer");
+    RPGP_REQUIRE(p->t_last >= 1, "plan_kmv_end: no product in flight (call rpgp_plan_kmv_begin first)");
+    RPGP_REQUIRE(0 <= row_begin && row_begin <= row_end && row_end <= p->n, "plan_kmv_end: rows [%lld, %lld) outside [0, %lld]",
+                 (long long)row_begin, (long long)row_end, p->n);
+    RPGP_CUDA_OK(cudaSetDevice(p->device));
+    cudaStream_t st = p->st;
+    const int t = p->t_last;
+    if (diag_add != 0.f)
+        if (int rc = launch_axpy_rows(diag_add, p->dV, t, p->n, t, p->dout, t, st)) return rc;
+    if (row_end > row_begin)
+        RPGP_CUDA_OK(cudaMemcpyAsync(out, p->dout + row_begin * t, (size_t)(row_end - row_begin) * t * 4, cudaMemcpyDeviceToHost, st));
+    RPGP_CUDA_OK(cudaStreamSynchronize(st));
+    p->t_last = 0;
+    return OK;
+}
+
 }  // extern "C"

@@ -220,8 +220,11 @@ __global__ void __launch_bounds__(128 * HALVES + 128, 2) mvm_sym_tc5_kernel(cons
         // =========================================== epilogue warps (+ MMA issue, + bulk copies) ========================
         asm volatile("setmaxnreg.dec.sync.aligned.u32 %0;" ::"n"(REGS_HELP));
         const int qd = warp - AW;                                  // TMEM lane quadrant (AW is a multiple of 4)
-        // two issuing threads (a UTCHMMA blocks its warp ~100 clk whatever its size): row side from quadrant 0, column side from quadrant 2
-        const bool row_issuer = (qd == 0 && lane == 0), col_issuer = (qd == 2 && lane == 0), loader = (qd == 1 && lane == 0);
+        // row-side MMAs from quadrant 0's warp, column-side MMAs from quadrant 2's, bulk copies from quadrant 1's.  Every lane of the
+        // warp follows the barriers and keeps the counters; the tcgen05.mma / commit / cp.async.bulk themselves are issued by one
+        // elected lane (elect_one, sym_tc_dev.cuh): warp-uniform control flow keeps the descriptors in uniform registers and the
+        // UTCHMMAs back to back (under `lane == 0` ptxas wraps each of them in a waterfall loop, ~150 clk per MMA)
+        const bool row_issuer = (qd == 0), col_issuer = (qd == 2), loader = (qd == 1);
         constexpr uint32_t IDESC_ROW_N32 = idesc5_tf32(128, 2 * T5_N, 0, 0), IDESC_ROW_N16 = idesc5_tf32(128, T5_N, 0, 0);
         constexpr uint32_t IDESC_COL = idesc5_tf32(64, 2 * T5_N, 1, 0);
         const unsigned char* bsplit = reinterpret_cast<const unsigned char*>(a.bsplit);
@@ -232,22 +235,31 @@ __global__ void __launch_bounds__(128 * HALVES + 128, 2) mvm_sym_tc5_kernel(cons
             const long long c0 = it.col0(tz);
             const uint32_t cols = (uint32_t)min((long long)T5_BN, a.n - c0);
             const int zs = jz % T5_ZST;
-            mbar_expect_tx(&bars[B5_ZFULL + zs], cols * CP * (uint32_t)sizeof(float));
-            bulk_g2s(sm + T5_Z + (uint32_t)zs * T5_BN * CP * 4u, zc + c0 * CP, cols * CP * (uint32_t)sizeof(float), &bars[B5_ZFULL + zs]);
+            if (elect_one()) {
+                mbar_expect_tx(&bars[B5_ZFULL + zs], cols * CP * (uint32_t)sizeof(float));
+                bulk_g2s(sm + T5_Z + (uint32_t)zs * T5_BN * CP * 4u, zc + c0 * CP, cols * CP * (uint32_t)sizeof(float), &bars[B5_ZFULL + zs]);
+            }
+            __syncwarp();
             tz = it.next_live(tz + 1);
             ++jz;
         };
         auto load_b = [&]() {
             const long long c0 = it.col0(tb);
             const int bs = jb & 1;
-            mbar_expect_tx(&bars[B5_BFULL + bs], 4096u);
-            bulk_g2s(sm + T5_BT + (uint32_t)bs * 4096u, bsplit + (c0 / T5_BN) * 4096, 4096u, &bars[B5_BFULL + bs]);
+            if (elect_one()) {
+                mbar_expect_tx(&bars[B5_BFULL + bs], 4096u);
+                bulk_g2s(sm + T5_BT + (uint32_t)bs * 4096u, bsplit + (c0 / T5_BN) * 4096, 4096u, &bars[B5_BFULL + bs]);
+            }
+            __syncwarp();
             tb = it.next_live(tb + 1);
             ++jb;
         };
         if (loader && tz < it.ntiles) {   // (a CTA without tiles must not leave copies in flight)
-            mbar_expect_tx(&bars[B5_BCFULL], 16384u);
-            bulk_g2s(sm + T5_BC, bsplit + (long long)it.I * 16384, 16384u, &bars[B5_BCFULL]);
+            if (elect_one()) {
+                mbar_expect_tx(&bars[B5_BCFULL], 16384u);
+                bulk_g2s(sm + T5_BC, bsplit + (long long)it.I * 16384, 16384u, &bars[B5_BCFULL]);
+            }
+            __syncwarp();
             for (int s = 0; s < T5_ZST && tz < it.ntiles; ++s) load_z();
             for (int s = 0; s < 2 && tb < it.ntiles; ++s) load_b();
         }
@@ -262,34 +274,40 @@ __global__ void __launch_bounds__(128 * HALVES + 128, 2) mvm_sym_tc5_kernel(cons
                 if (j % T5_F == 0 && e >= 2) mbar5_wait_sleep(&bars[B5_D1EMPTY + (e & 1)], (uint32_t)(((e >> 1) - 1) & 1));
                 mbar5_wait_sleep(&bars[B5_SFULL + b], (uint32_t)((j >> 1) & 1));
                 tc5_fence_after();
-                if (!(T5_DIAG & 4)) {
-                    const uint32_t sbuf = base + T5_S + (uint32_t)b * 32768u;
-                    const uint32_t d1 = tmem + 32u * (uint32_t)(e & 1);
-                    const uint64_t dA_h = smem_desc5(sbuf, 512, 512, LAYOUT5_SW128_BASE32B);
-                    const uint64_t dA_l = smem_desc5(sbuf + 16384u, 512, 512, LAYOUT5_SW128_BASE32B);
-                    const uint64_t dB = smem_desc5(base + T5_BT + (uint32_t)b * 4096u, 16, 1024, LAYOUT5_SW128);
+                if (elect_one()) {
+                    if (!(T5_DIAG & 4)) {
+                        const uint32_t sbuf = base + T5_S + (uint32_t)b * 32768u;
+                        const uint32_t d1 = tmem + 32u * (uint32_t)(e & 1);
+                        const uint64_t dA_h = smem_desc5(sbuf, 512, 512, LAYOUT5_SW128_BASE32B);
+                        const uint64_t dA_l = smem_desc5(sbuf + 16384u, 512, 512, LAYOUT5_SW128_BASE32B);
+                        const uint64_t dB = smem_desc5(base + T5_BT + (uint32_t)b * 4096u, 16, 1024, LAYOUT5_SW128);
 #pragma unroll
-                    for (int ks = 0; ks < 4; ++ks) {
-                        umma5(d1, dA_h + (uint64_t)(ks * 2), dB + (uint64_t)(ks * 2), IDESC_ROW_N32, (j % T5_F != 0 || ks > 0) ? 1u : 0u);
-                        umma5(d1, dA_l + (uint64_t)(ks * 2), dB + (uint64_t)(ks * 2), IDESC_ROW_N16, 1u);
+                        for (int ks = 0; ks < 4; ++ks) {
+                            umma5(d1, dA_h + (uint64_t)(ks * 2), dB + (uint64_t)(ks * 2), IDESC_ROW_N32, (j % T5_F != 0 || ks > 0) ? 1u : 0u);
+                            umma5(d1, dA_l + (uint64_t)(ks * 2), dB + (uint64_t)(ks * 2), IDESC_ROW_N16, 1u);
+                        }
                     }
+                    umma5_commit(&bars[B5_TDONE + b]);
                 }
-                umma5_commit(&bars[B5_TDONE + b]);
+                __syncwarp();
             }
             if (col_issuer) {   // D2 = [Sh ; Sl]^T . [Vh|Vl], sixteen k-steps of 8 tile rows (nothing to do on the diagonal block)
                 if (j == 0) mbar5_wait_sleep(&bars[B5_BCFULL], 0u);
                 if (j >= 2) mbar5_wait_sleep(&bars[B5_EREAD + b], (uint32_t)(((j >> 1) - 1) & 1));        // D2[b] has been read
                 mbar5_wait_sleep(&bars[B5_SFULL + b], (uint32_t)((j >> 1) & 1));
                 tc5_fence_after();
-                if (!diag && !(T5_DIAG & 2)) {
-                    const uint32_t d2 = tmem + 64u + 32u * (uint32_t)b;
-                    const uint64_t dA = smem_desc5(base + T5_S + (uint32_t)b * 32768u, 16384, 512, LAYOUT5_SW128_BASE32B);
-                    const uint64_t dB = smem_desc5(base + T5_BC, 16, 1024, LAYOUT5_SW128);
+                if (elect_one()) {
+                    if (!diag && !(T5_DIAG & 2)) {
+                        const uint32_t d2 = tmem + 64u + 32u * (uint32_t)b;
+                        const uint64_t dA = smem_desc5(base + T5_S + (uint32_t)b * 32768u, 16384, 512, LAYOUT5_SW128_BASE32B);
+                        const uint64_t dB = smem_desc5(base + T5_BC, 16, 1024, LAYOUT5_SW128);
 #pragma unroll
-                    for (int g = 0; g < 16; ++g)
-                        umma5(d2, dA + (uint64_t)((g * 1024) >> 4), dB + (uint64_t)(((g >> 2) * 4096 + (g & 3) * 32) >> 4), IDESC_COL, g > 0 ? 1u : 0u);
+                        for (int g = 0; g < 16; ++g)
+                            umma5(d2, dA + (uint64_t)((g * 1024) >> 4), dB + (uint64_t)(((g >> 2) * 4096 + (g & 3) * 32) >> 4), IDESC_COL, g > 0 ? 1u : 0u);
+                    }
+                    umma5_commit(&bars[B5_TDONE + b]);
                 }
-                umma5_commit(&bars[B5_TDONE + b]);
+                __syncwarp();
             }
             __syncwarp();
             mbar5_wait_sleep(&bars[B5_TDONE + b], (uint32_t)((j >> 1) & 1));

@@ -51,6 +51,16 @@ __device__ __forceinline__ void mbar5_wait_sleep(uint64_t* bar, uint32_t parity)
         __nanosleep(NS_SLEEP);
     }
 }
+// One lane of a converged warp (elect.sync).  Issuing tcgen05.mma / tcgen05.commit / cp.async.bulk under this predicate -- instead of
+// under `lane == 0` -- lets ptxas keep the descriptors in uniform registers and emit the UTCHMMAs back to back: in code it must assume
+// divergent it wraps EVERY uniform-datapath instruction in an ELECT / BRA.U.ANY waterfall loop whose branch waits for the
+// instruction's scoreboard (the "~150 clk per MMA, per issuing warp" of profiles/umma_microbench_r01.txt; SASS in
+// profiles/umma_issue_r02.txt).  Every lane of the warp must reach the call.
+__device__ __forceinline__ bool elect_one() {
+    uint32_t pred;
+    asm volatile("{\n\t.reg .pred px;\n\telect.sync _|px, 0xFFFFFFFF;\n\tselp.u32 %0, 1, 0, px;\n\t}\n" : "=r"(pred));
+    return pred != 0;
+}
 __device__ __forceinline__ void tc5_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
 __device__ __forceinline__ void tc5_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
 __device__ __forceinline__ void fence5_async_smem() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }

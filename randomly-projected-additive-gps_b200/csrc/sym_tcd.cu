@@ -346,7 +346,7 @@ __global__ void __maxnreg__(80) mvm_sym_tcd_kernel(const SymDArgs a) {
     } else if (warp < D_AW + 4) {
         // =========================================== epilogue warps (+ bulk copies) =====================================
         const int qd = warp - D_AW;                                // TMEM lane quadrant
-        const bool loader = (qd == 1 && lane == 0);
+        const bool loader = (qd == 1);      // the whole warp keeps the copy counters; one elected lane issues (elect_one: no waterfall loops)
         const unsigned char* bsplit = reinterpret_cast<const unsigned char*>(a.bsplit);
         const unsigned char* bimg = a.bimg + (size_t)chunk * a.nblocks * 4 * NL * 8192;
 
@@ -355,24 +355,33 @@ __global__ void __maxnreg__(80) mvm_sym_tcd_kernel(const SymDArgs a) {
         auto load_z = [&]() {
             const long long c0 = it.col0(tz);
             const int zs = jz % D_ZST;
-            mbar_expect_tx(&bars[BD_ZFULL + zs], (uint32_t)NL * 8192u);
-            bulk_g2s(sm + d_bimg(NL) + (uint32_t)zs * NL * 8192u, bimg + (size_t)(c0 / T5_BN) * NL * 8192, (uint32_t)NL * 8192u, &bars[BD_ZFULL + zs]);
+            if (elect_one()) {
+                mbar_expect_tx(&bars[BD_ZFULL + zs], (uint32_t)NL * 8192u);
+                bulk_g2s(sm + d_bimg(NL) + (uint32_t)zs * NL * 8192u, bimg + (size_t)(c0 / T5_BN) * NL * 8192, (uint32_t)NL * 8192u, &bars[BD_ZFULL + zs]);
+            }
+            __syncwarp();
             tz = it.next_live(tz + 1);
             ++jz;
         };
         auto load_b = [&]() {
             const long long c0 = it.col0(tb);
             const int bs = jb & 1;
-            mbar_expect_tx(&bars[BD_BFULL + bs], 4096u);
-            bulk_g2s(sm + D_BT + (uint32_t)bs * 4096u, bsplit + (c0 / T5_BN) * 4096, 4096u, &bars[BD_BFULL + bs]);
+            if (elect_one()) {
+                mbar_expect_tx(&bars[BD_BFULL + bs], 4096u);
+                bulk_g2s(sm + D_BT + (uint32_t)bs * 4096u, bsplit + (c0 / T5_BN) * 4096, 4096u, &bars[BD_BFULL + bs]);
+            }
+            __syncwarp();
             tb = it.next_live(tb + 1);
             ++jb;
         };
         if (loader && tz < it.ntiles) {   // (a CTA without tiles must not leave copies in flight)
-            mbar_expect_tx(&bars[BD_AFULL], (uint32_t)NL * 32768u);
-            bulk_g2s(sm + D_AIMG, a.aimg + ((size_t)chunk * a.nblocks + it.I) * NL * 32768, (uint32_t)NL * 32768u, &bars[BD_AFULL]);
-            mbar_expect_tx(&bars[BD_BCFULL], 16384u);
-            bulk_g2s(sm + D_BC, bsplit + (long long)it.I * 16384, 16384u, &bars[BD_BCFULL]);
+            if (elect_one()) {
+                mbar_expect_tx(&bars[BD_AFULL], (uint32_t)NL * 32768u);
+                bulk_g2s(sm + D_AIMG, a.aimg + ((size_t)chunk * a.nblocks + it.I) * NL * 32768, (uint32_t)NL * 32768u, &bars[BD_AFULL]);
+                mbar_expect_tx(&bars[BD_BCFULL], 16384u);
+                bulk_g2s(sm + D_BC, bsplit + (long long)it.I * 16384, 16384u, &bars[BD_BCFULL]);
+            }
+            __syncwarp();
             for (int s = 0; s < D_ZST && tz < it.ntiles; ++s) load_z();
             for (int s = 0; s < 2 && tb < it.ntiles; ++s) load_b();
         }
@@ -425,7 +434,9 @@ __global__ void __maxnreg__(80) mvm_sym_tcd_kernel(const SymDArgs a) {
         // them does anything else: role 0 row side, roles 1/2 column side (tile rows 0..63 / 64..127), roles 3.. distances
         const int role = warp - D_AW - 4;
         const bool has_tiles = it.next_live(0) < it.ntiles;
-        if (lane == 0 && has_tiles && role == 0) {
+        // every lane of an issuing warp follows the barriers; the MMAs and their commit are issued under elect.sync (elect_one):
+        // warp-uniform control flow lets ptxas emit the UTCHMMAs back to back from uniform registers (sym_tc_dev.cuh)
+        if (has_tiles && role == 0) {
             constexpr uint32_t IDESC_ROW_N32 = idesc5_tf32(128, 2 * T5_N, 0, 0), IDESC_ROW_N16 = idesc5_tf32(128, T5_N, 0, 0);
             int j = 0;
             for (int t = it.next_live(0); t < it.ntiles; t = it.next_live(t + 1), ++j) {   // D1 += Sh.[Vh|Vl] + Sl.Vh, four k-steps of 8 tile columns
@@ -434,20 +445,23 @@ __global__ void __maxnreg__(80) mvm_sym_tcd_kernel(const SymDArgs a) {
                 if (j % D_F == 0 && e >= 2) mbar_wait_ns(a.sleep_ns, &bars[BD_D1EMPTY + (e & 1)], (uint32_t)(((e >> 1) - 1) & 1));
                 mbar_wait_ns(a.sleep_ns, &bars[BD_SFULL + b], (uint32_t)((j >> 1) & 1));
                 tc5_fence_after();
-                const uint32_t sbuf = base + D_S + (uint32_t)b * 32768u;
-                const uint32_t d1 = tmem + D_TM_D1 + 32u * (uint32_t)(e & 1);
-                const uint64_t dA_h = smem_desc5(sbuf, 512, 512, LAYOUT5_SW128_BASE32B);
-                const uint64_t dA_l = smem_desc5(sbuf + 16384u, 512, 512, LAYOUT5_SW128_BASE32B);
-                const uint64_t dB = smem_desc5(base + D_BT + (uint32_t)b * 4096u, 16, 1024, LAYOUT5_SW128);
+                if (elect_one()) {
+                    const uint32_t sbuf = base + D_S + (uint32_t)b * 32768u;
+                    const uint32_t d1 = tmem + D_TM_D1 + 32u * (uint32_t)(e & 1);
+                    const uint64_t dA_h = smem_desc5(sbuf, 512, 512, LAYOUT5_SW128_BASE32B);
+                    const uint64_t dA_l = smem_desc5(sbuf + 16384u, 512, 512, LAYOUT5_SW128_BASE32B);
+                    const uint64_t dB = smem_desc5(base + D_BT + (uint32_t)b * 4096u, 16, 1024, LAYOUT5_SW128);
 #pragma unroll
-                for (int ks = 0; ks < 4; ++ks) {
-                    if (TCD_DIAG & 4) break;
-                    umma5(d1, dA_h + (uint64_t)(ks * 2), dB + (uint64_t)(ks * 2), IDESC_ROW_N32, (j % D_F != 0 || ks > 0) ? 1u : 0u);
-                    umma5(d1, dA_l + (uint64_t)(ks * 2), dB + (uint64_t)(ks * 2), IDESC_ROW_N16, 1u);
+                    for (int ks = 0; ks < 4; ++ks) {
+                        if (TCD_DIAG & 4) break;
+                        umma5(d1, dA_h + (uint64_t)(ks * 2), dB + (uint64_t)(ks * 2), IDESC_ROW_N32, (j % D_F != 0 || ks > 0) ? 1u : 0u);
+                        umma5(d1, dA_l + (uint64_t)(ks * 2), dB + (uint64_t)(ks * 2), IDESC_ROW_N16, 1u);
+                    }
+                    umma5_commit(&bars[BD_TDONE + b]);
                 }
-                umma5_commit(&bars[BD_TDONE + b]);
+                __syncwarp();
             }
-        } else if (lane == 0 && has_tiles && role == 1) {
+        } else if (has_tiles && role == 1) {
             constexpr uint32_t IDESC_COL = idesc5_tf32(64, 2 * T5_N, 1, 0);
             mbar_wait_ns(a.sleep_ns, &bars[BD_BCFULL], 0u);
             int j = 0;
@@ -456,17 +470,21 @@ __global__ void __maxnreg__(80) mvm_sym_tcd_kernel(const SymDArgs a) {
                 if (j >= 2) mbar_wait_ns(a.sleep_ns, &bars[BD_EREAD + b], (uint32_t)(((j >> 1) - 1) & 1));        // D2[b] has been read
                 mbar_wait_ns(a.sleep_ns, &bars[BD_SFULL + b], (uint32_t)((j >> 1) & 1));
                 tc5_fence_after();
-                if (!it.diag(t) && !(TCD_DIAG & 2)) {      // (nothing to do on the diagonal block)
-                    const uint32_t d2 = tmem + D_TM_D2 + 32u * (uint32_t)b;
-                    const uint64_t dA = smem_desc5(base + D_S + (uint32_t)b * 32768u, 16384, 512, LAYOUT5_SW128_BASE32B);
-                    const uint64_t dB = smem_desc5(base + D_BC, 16, 1024, LAYOUT5_SW128);
+                const bool work = !it.diag(t) && !(TCD_DIAG & 2);      // (nothing to do on the diagonal block)
+                if (elect_one()) {
+                    if (work) {
+                        const uint32_t d2 = tmem + D_TM_D2 + 32u * (uint32_t)b;
+                        const uint64_t dA = smem_desc5(base + D_S + (uint32_t)b * 32768u, 16384, 512, LAYOUT5_SW128_BASE32B);
+                        const uint64_t dB = smem_desc5(base + D_BC, 16, 1024, LAYOUT5_SW128);
 #pragma unroll
-                    for (int g = 0; g < 16; ++g)
-                        umma5(d2, dA + (uint64_t)((g * 1024) >> 4), dB + (uint64_t)(((g >> 2) * 4096 + (g & 3) * 32) >> 4), IDESC_COL, g > 0 ? 1u : 0u);
+                        for (int g = 0; g < 16; ++g)
+                            umma5(d2, dA + (uint64_t)((g * 1024) >> 4), dB + (uint64_t)(((g >> 2) * 4096 + (g & 3) * 32) >> 4), IDESC_COL, g > 0 ? 1u : 0u);
+                    }
+                    umma5_commit(&bars[BD_TDONE + b]);
                 }
-                umma5_commit(&bars[BD_TDONE + b]);
+                __syncwarp();
             }
-        } else if (lane == 0 && has_tiles && role - 2 < D_NDI) {
+        } else if (has_tiles && role - 2 < D_NDI) {
             // issuer w owns the groups w, w + D_NDI, .. of every batch: U = Ah.Bh + Al.Bh + Ah.Bl into the batch's D0 columns, KS k-steps each
             const int w = role - 2;
             constexpr uint32_t IDESC_D0 = idesc5_tf32(128, T5_BN, 0, 0);
@@ -486,22 +504,25 @@ __global__ void __maxnreg__(80) mvm_sym_tcd_kernel(const SymDArgs a) {
                         mbar_wait_ns(a.sleep_ns, &bars[BD_D0FREE + buf], (use - 1) & 1u);
                         tc5_fence_after();
                     }
-                    if (g < G) {
-                        const uint32_t d0 = tmem + D_TM_D0 + 64u * buf + 32u * (uint32_t)w;
-                        for (int ks = 0; ks < ((TCD_DIAG & 8) ? 0 : KS); ++ks) {
-                            const int ksi = g * KS + ks;
-                            const uint32_t l = (uint32_t)(ksi >> 2);
-                            const uint64_t o = (uint64_t)((ksi & 3) * 2);
-                            const uint64_t dAh = smem_desc5(base + D_AIMG + l * 32768u, 16, 1024, LAYOUT5_SW128) + o;
-                            const uint64_t dAl = smem_desc5(base + D_AIMG + l * 32768u + 16384u, 16, 1024, LAYOUT5_SW128) + o;
-                            const uint64_t dBh = smem_desc5(bst + l * 8192u, 16, 1024, LAYOUT5_SW128) + o;
-                            const uint64_t dBl = smem_desc5(bst + l * 8192u + 4096u, 16, 1024, LAYOUT5_SW128) + o;
-                            umma5(d0, dAh, dBh, IDESC_D0, ks > 0 ? 1u : 0u);
-                            umma5(d0, dAl, dBh, IDESC_D0, 1u);
-                            umma5(d0, dAh, dBl, IDESC_D0, 1u);
+                    if (elect_one()) {
+                        if (g < G) {
+                            const uint32_t d0 = tmem + D_TM_D0 + 64u * buf + 32u * (uint32_t)w;
+                            for (int ks = 0; ks < ((TCD_DIAG & 8) ? 0 : KS); ++ks) {
+                                const int ksi = g * KS + ks;
+                                const uint32_t l = (uint32_t)(ksi >> 2);
+                                const uint64_t o = (uint64_t)((ksi & 3) * 2);
+                                const uint64_t dAh = smem_desc5(base + D_AIMG + l * 32768u, 16, 1024, LAYOUT5_SW128) + o;
+                                const uint64_t dAl = smem_desc5(base + D_AIMG + l * 32768u + 16384u, 16, 1024, LAYOUT5_SW128) + o;
+                                const uint64_t dBh = smem_desc5(bst + l * 8192u, 16, 1024, LAYOUT5_SW128) + o;
+                                const uint64_t dBl = smem_desc5(bst + l * 8192u + 4096u, 16, 1024, LAYOUT5_SW128) + o;
+                                umma5(d0, dAh, dBh, IDESC_D0, ks > 0 ? 1u : 0u);
+                                umma5(d0, dAl, dBh, IDESC_D0, 1u);
+                                umma5(d0, dAh, dBl, IDESC_D0, 1u);
+                            }
                         }
+                        umma5_commit(&bars[BD_D0FULL + buf]);      // (an issuer without a group in this batch still reports)
                     }
-                    umma5_commit(&bars[BD_D0FULL + buf]);      // (an issuer without a group in this batch still reports)
+                    __syncwarp();
                 }
             }
         }

@@ -73,6 +73,12 @@ SIGNATURES = {
     "rpgp_kmv_host_f32": (c_int, [c_void_p, c_int64, c_void_p, c_int64, c_int, c_void_p, c_int, c_int, c_void_p,
                                   c_void_p, c_void_p, c_void_p, c_int, c_float, c_void_p, c_int]),
     "rpgp_measure_peaks": (c_int, [POINTER(c_double), c_int, POINTER(c_char_p)]),
+    "rpgp_plan_create": (c_int, [c_int64, c_int, c_int, c_int, c_int, c_int, c_void_p, POINTER(c_void_p)]),
+    "rpgp_plan_destroy": (c_int, [c_void_p]),
+    "rpgp_plan_set_operator": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p]),
+    "rpgp_plan_kmv_begin": (c_int, [c_void_p, c_void_p, c_int, c_int, c_int]),
+    "rpgp_plan_device_out": (c_void_p, [c_void_p]),
+    "rpgp_plan_kmv_end": (c_int, [c_void_p, c_float, c_void_p, c_int64, c_int64]),
 }
 
 _lib = None
@@ -168,6 +174,51 @@ def free_workspaces():
     _workspaces.clear()
 
 
+# ---- optional per-call device timing (bench.py's kernel split of an MLL step) ----------------------------------------------
+_timing = None
+
+
+class timing:
+    """with _lib.timing() as tm: ... ; tm.totals() -> {entry point: (calls, ms)} from CUDA events recorded around every library
+    call made on the current stream inside the block (synchronises once, when totals() is read)."""
+
+    def __enter__(self):
+        global _timing
+        self.records, self._prev = [], _timing
+        _timing = self
+        return self
+
+    def __exit__(self, *exc):
+        global _timing
+        _timing = self._prev
+
+    def totals(self):
+        torch.cuda.synchronize()
+        out = {}
+        for name, e0, e1 in self.records:
+            calls, ms = out.get(name, (0, 0.0))
+            out[name] = (calls + 1, ms + e0.elapsed_time(e1))
+        return out
+
+
+class _timed:
+    __slots__ = ("name", "e1")
+
+    def __init__(self, name):
+        self.name = name
+
+    def __enter__(self):
+        if _timing is not None:
+            e0, self.e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            _timing.records.append((self.name, e0, self.e1))
+            e0.record()
+        return self
+
+    def __exit__(self, *exc):
+        if _timing is not None:
+            self.e1.record()
+
+
 # ---- thin wrappers ------------------------------------------------------------------------------------------------------
 def pack_coords(Z, lay, scale=None):
     """natural (n x J*K) float32 CUDA tensor -> packed planes (nchunks, n, CP), scaled."""
@@ -233,7 +284,7 @@ def mvm_fwd(z1p, z2p, lay, nlc, V, row_range=None, events=None):
     out = torch.empty((m, t), dtype=torch.float32, device=V.device)
     tmax = max_rhs(lay, False)
     z1_ptr = c_void_p(z1p.data_ptr() + r0 * lay.CP * 4)
-    with torch.cuda.device(V.device):
+    with torch.cuda.device(V.device), _timed("mvm_fwd"):
         st = _stream(V.device)
         for t0 in range(0, t, tmax):
             tc = min(tmax, t - t0)
@@ -277,7 +328,7 @@ def mvm_sym(zp, lay, nlc, V, block_range=None, events=None):
     nblocks = (n + 127) // 128
     b0, b1 = (0, nblocks) if block_range is None else block_range
     out = torch.empty((n, t), dtype=torch.float32, device=V.device)
-    with torch.cuda.device(V.device):
+    with torch.cuda.device(V.device), _timed("mvm_sym"):
         st = _stream(V.device)
         for t0 in range(0, t, 16):
             tc = min(16, t - t0)
@@ -311,7 +362,7 @@ def quad_bwd(z1p, z2p, lay, nlc, L, R, symmetric, row_range=None, L_full=None, R
     dz = None
     g = None
     z1_ptr = c_void_p(z1p.data_ptr() + r0 * lay.CP * 4)
-    with torch.cuda.device(L.device):
+    with torch.cuda.device(L.device), _timed("quad_bwd"):
         st = _stream(L.device)
         for t0 in range(0, t, tmax):
             tc = min(tmax, t - t0)
@@ -401,6 +452,81 @@ def kmv_host(X1, X2, W, J, K, pre_inv, post_inv, c, V, diag_add=0.0, device=0):
     _check(load().rpgp_kmv_host_f32(p(X1), m, p(X2), n, d, p(W), J, K, p(pre_inv), p(post_inv), p(c), p(V), t,
                                     float(diag_add), p(out), int(device)), "rpgp_kmv_host_f32")
     return out
+
+
+class _DevicePointer:
+    """a borrowed device buffer for torch.as_tensor (CUDA array interface, float32, C-contiguous)"""
+
+    def __init__(self, ptr, shape):
+        self.__cuda_array_interface__ = {"shape": tuple(shape), "typestr": "<f4", "data": (int(ptr), False), "version": 3,
+                                         "strides": None}
+
+
+class HostPlan:
+    """The host-buffer path as a persistent plan (rpgp_plan_*, include/rpgp.h): device buffers allocated once; per step
+    `set_operator` (H2D of X, W, scales, c + projection), `kmv` (H2D of V, symmetric product of this rank's block pairs,
+    all-reduce over the ranks of the default process group when there are several, + sigma^2 V, D2H of the rank's rows).
+    numpy float32 arrays in, numpy out; pinned arrays (torch `.pin_memory().numpy()`) make the copies full-speed."""
+
+    def __init__(self, n, d, J, K, tmax, device=0):
+        self.n, self.d, self.J, self.K, self.tmax, self.device = int(n), int(d), int(J), int(K), int(tmax), int(device)
+        self._h = c_void_p()
+        with torch.cuda.device(self.device):
+            self._stream = torch.cuda.current_stream(self.device)
+            _check(load().rpgp_plan_create(self.n, self.d, self.J, self.K, self.tmax, self.device,
+                                           c_void_p(self._stream.cuda_stream), ctypes.byref(self._h)), "rpgp_plan_create")
+        self._keep = None
+
+    def close(self):
+        if self._h:
+            load().rpgp_plan_destroy(self._h)
+            self._h = c_void_p()
+
+    __del__ = close
+
+    @staticmethod
+    def _p(a):
+        return None if a is None else a.ctypes.data_as(c_void_p)
+
+    @staticmethod
+    def _arr(a, shape=None):
+        import numpy as np
+        if a is None:
+            return None
+        a = np.ascontiguousarray(a, dtype=np.float32)
+        if shape is not None and tuple(a.shape) != tuple(shape):
+            raise ValueError("expected shape %s, got %s" % (tuple(shape), tuple(a.shape)))
+        return a
+
+    def set_operator(self, X, W, pre_inv, post_inv, c):
+        X, W, c = self._arr(X, (self.n, self.d)), self._arr(W, (self.J * self.K, self.d)), self._arr(c, (self.J,))
+        pre_inv, post_inv = self._arr(pre_inv), self._arr(post_inv)
+        self._keep = (X, W, pre_inv, post_inv, c)       # asynchronous copies: keep the host arrays alive
+        _check(load().rpgp_plan_set_operator(self._h, self._p(X), self._p(W), self._p(pre_inv), self._p(post_inv), self._p(c)),
+               "rpgp_plan_set_operator")
+
+    def kmv(self, V, diag_add=0.0, block_range=None, row_range=None, all_reduce=None, out=None):
+        """K(X,X) V + diag_add V.  block_range: this rank's 128-row blocks (default: all); all_reduce: callable applied to
+        the device product (a torch view of the plan's buffer) between the kernel and the copy back; row_range: rows returned;
+        out: optional (rows x t) float32 array to receive them (pinned: full-speed copy)."""
+        import numpy as np
+        V = self._arr(V)
+        t = V.shape[1]
+        nblocks = (self.n + 127) // 128
+        b0, b1 = (0, nblocks) if block_range is None else block_range
+        r0, r1 = (0, self.n) if row_range is None else row_range
+        lib = load()
+        _check(lib.rpgp_plan_kmv_begin(self._h, self._p(V), t, int(b0), int(b1)), "rpgp_plan_kmv_begin")
+        if all_reduce is not None:
+            with torch.cuda.device(self.device):
+                dev_out = torch.as_tensor(_DevicePointer(lib.rpgp_plan_device_out(self._h), (self.n, t)),
+                                          device=torch.device("cuda", self.device))
+                all_reduce(dev_out)
+        if out is None:
+            out = np.empty((r1 - r0, t), dtype=np.float32)
+        assert out.dtype == np.float32 and out.shape == (r1 - r0, t) and out.flags["C_CONTIGUOUS"]
+        _check(lib.rpgp_plan_kmv_end(self._h, float(diag_add), self._p(out), int(r0), int(r1)), "rpgp_plan_kmv_end")
+        return out
 
 
 def measure_peaks():

@@ -3,7 +3,10 @@
 One process per GPU (torchrun); rank r owns the contiguous rows [r*ceil(n/G), (r+1)*ceil(n/G)) of K.  X, W, the
 hyper-parameters and the CG state are replicated, so Z^ is computed redundantly on every rank (no exchange) and every
 CG iteration needs exactly one collective: an all-gather of the (n/G x t) row blocks of K.P (NCCL over NVLink on GPUs;
-gloo in the CPU tests).  Gradients: the rows' dZ^ are all-gathered once per step, the J outputscale partials are
+gloo in the CPU tests) -- or, with the symmetric tensor-core kernel, an all-reduce of the partial products.
+REPLICATION CONTRACT: every rank must hold bit-identical X, y, hyper-parameters and right-hand sides.  Random draws made
+inside the solver (the SLQ probe vectors) are drawn on rank 0 and broadcast (`broadcast_`); `assert_replicated` checks the
+operands of every MLL solve and raises when ranks disagree (differently seeded ranks used to give silently wrong results).  Gradients: the rows' dZ^ are all-gathered once per step, the J outputscale partials are
 all-reduced.  This replaces gpytorch.kernels.MultiDeviceKernel (training_routines.py:407-408), which scatters x1 over
 devices inside one process and copies row blocks back through peer memcpys.
 """
@@ -62,6 +65,35 @@ def all_gather_rows(block, part):
     full = block.new_empty((part.block * part.world,) + tuple(t))
     tdist.all_gather_into_tensor(full, block.contiguous())
     return full[:part.n]
+
+
+def broadcast_(x, src=0):
+    """in-place broadcast from rank `src` (random draws -- SLQ probes, initial values -- must be IDENTICAL on every rank: the CG
+    state is replicated, and a rank multiplying different vectors would all-reduce garbage without any error)"""
+    if world_size() > 1:
+        tdist.broadcast(x, src=src)
+    return x
+
+
+def assert_replicated(what, *tensors, rtol=0.0):
+    """Raise if a tensor that must be replicated differs between ranks (checksum = float64 sum and sum of squares, compared
+    exactly by default).  One small all-gather; called once per solve on the right-hand sides and the operator's representation."""
+    if world_size() == 1:
+        return
+    sums = []
+    for t in tensors:
+        td = t.detach().double()
+        sums += [td.sum(), (td * td).sum()]
+    mine = torch.stack(sums)
+    allv = [torch.empty_like(mine) for _ in range(world_size())]
+    tdist.all_gather(allv, mine)
+    ref = allv[0]
+    for r, v in enumerate(allv):
+        bad = (v - ref).abs() > rtol * ref.abs()
+        if bool(bad.any()):
+            raise RuntimeError("rpgp.dist: %s differs between rank 0 and rank %d (checksums %s vs %s): every rank must hold identical "
+                               "replicated state -- seed all ranks identically or broadcast the random draws" %
+                               (what, r, ref.tolist(), v.tolist()))
 
 
 def all_reduce_sum(x):

@@ -14,6 +14,7 @@ with ordinary autograd through the differentiable dense evaluation.
 """
 import torch
 
+from .. import dist as rdist
 from .preconditioner import slq_logdet
 
 
@@ -28,6 +29,8 @@ class _InvQuadLogDetCG(torch.autograd.Function):
         s = _settings()
         op = op_template._rebuild(*[r.detach() for r in rep])
         n = op.shape[-1]
+        if rdist.world_size() > 1:
+            rdist.assert_replicated("the MLL solve's right-hand side / operator representation", rhs, *[r for r in rep if torch.is_tensor(r)])
         dtype, device = rhs.dtype, rhs.device
         precond = op._preconditioner()
         num_probes = s.num_trace_samples.value() if compute_logdet else 0
@@ -40,6 +43,8 @@ class _InvQuadLogDetCG(torch.autograd.Function):
                 probes = torch.randn(n, num_probes, dtype=dtype, device=device)
             else:
                 probes = precond.sample(num_probes).to(dtype)
+            if rdist.world_size() > 1:      # one set of probes for the whole job (local RNG streams differ)
+                probes = rdist.broadcast_(probes.contiguous())
             norms = probes.norm(2, dim=-2, keepdim=True)
             probes = probes / norms
             full_rhs = torch.cat([probes, rhs], dim=-1)

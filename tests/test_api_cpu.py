@@ -39,6 +39,19 @@ def test_library_exports_every_declared_symbol():
     assert _lib.load().rpgp_version() >= 100
 
 
+def test_plan_handle_argument_checks_need_no_gpu():
+    """rpgp_plan_create validates its shape arguments before touching the device; a NULL plan is rejected by every entry point"""
+    lib = _lib.load()
+    h = ctypes.c_void_p()
+    rc = lib.rpgp_plan_create(0, 3, 2, 1, 4, 0, None, ctypes.byref(h))
+    assert rc == 1 and b"bad shape" in lib.rpgp_last_error() and not h
+    assert lib.rpgp_plan_kmv_begin(None, None, 1, 0, 0) == 1
+    assert lib.rpgp_plan_kmv_end(None, 0.0, None, 0, 0) == 1
+    assert lib.rpgp_plan_set_operator(None, None, None, None, None, None) == 1
+    assert lib.rpgp_plan_device_out(None) is None
+    assert lib.rpgp_plan_destroy(None) == 0
+
+
 def test_layout_planner_host_logic():
     for (J, K) in [(20, 1), (26, 1), (1, 1), (90, 1), (33, 1), (1, 20), (20, 5), (3, 2), (4, 3), (2, 32), (5, 8)]:
         lay = _lib.plan_layout(J, K)

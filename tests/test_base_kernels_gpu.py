@@ -18,9 +18,7 @@ pytestmark = pytest.mark.gpu
 DEV = torch.device("cuda:0")
 
 
-def rel(a, b):
-    a, b = np.asarray(a, np.float64), np.asarray(b, np.float64)
-    return np.linalg.norm(a - b) / max(np.linalg.norm(b), 1e-300)
+from parity_util import rel  # noqa: E402  (norm-wise error; its repr adds the row-wise / element-wise figures)
 
 
 def data(m, n, J, K, t, seed):

@@ -13,10 +13,7 @@ from rpgp import _lib
 pytestmark = pytest.mark.gpu
 
 
-def rel(a, b):
-    a = np.asarray(a, dtype=np.float64)
-    b = np.asarray(b, dtype=np.float64)
-    return np.linalg.norm(a - b) / max(np.linalg.norm(b), 1e-300)
+from parity_util import rel  # noqa: E402  (norm-wise error; its repr adds the row-wise / element-wise figures)
 
 
 def make_problem(m, n, J, K, t, seed, spread=1.0, equal_c=False):
@@ -199,3 +196,38 @@ def test_error_reporting():
     with pytest.raises(RuntimeError, match="status"):
         bad = _lib.Layout(20, 1, 7, 1, 1, 7)
         _lib.pack_log2c(torch.ones(20, device=dev), bad)
+
+
+# ---- the host-buffer path as a persistent plan (rpgp_plan_*; bench.py's e2e) ------------------------------------------------------
+@pytest.mark.parametrize("n,d,J,K,t", [(3000, 10, 20, 1, 11), (700, 6, 5, 1, 3), (2600, 12, 4, 5, 11), (1500, 8, 26, 1, 16)])
+def test_host_plan_matches_oracle_and_block_shares_sum_to_full(n, d, J, K, t):
+    """set_operator (H2D + projection) then kmv (H2D of V, symmetric product, + sigma^2 V, D2H) through the plan handle: the product
+    against the FP64 oracle, the one-shot rpgp_kmv_host_f32, and three uneven rank shares summed on the host"""
+    rng = np.random.RandomState(n + J)
+    X = rng.randn(n, d).astype(np.float32)
+    W = (rng.randn(J * K, d) / np.sqrt(K * d) * 2.0).astype(np.float32)
+    ell = (0.5 + rng.rand(d)).astype(np.float32)
+    c = (rng.rand(J) + 0.1).astype(np.float32)
+    V = rng.randn(n, t).astype(np.float32)
+    Z = orc.scaled_projection(X, W, ell, prescale=True)
+    ref = orc.kmv(Z, Z, c, J, K, V) + 0.25 * V.astype(np.float64)
+    plan = _lib.HostPlan(n, d, J, K, t, device=0)
+    try:
+        plan.set_operator(X, W, 1.0 / ell, None, c)
+        got = plan.kmv(V, diag_add=0.25)
+        assert rel(got, ref) < 1e-5, rel(got, ref)
+        again = plan.kmv(V[:, :max(1, t // 2)], diag_add=0.25)               # fewer right-hand sides through the same plan
+        assert rel(again, ref[:, :max(1, t // 2)]) < 1e-5
+        one_shot = _lib.kmv_host(X, None, W, J, K, 1.0 / ell, None, c, V, diag_add=0.25, device=0)
+        assert rel(got, one_shot) < 2e-6, rel(got, one_shot)
+        nb = (n + 127) // 128
+        cuts = [0, nb // 3, nb // 3 + 1, nb]
+        parts = sum(plan.kmv(V, block_range=(cuts[r], cuts[r + 1])).astype(np.float64) for r in range(3))
+        assert rel(parts + 0.25 * V, ref) < 1e-5
+        rows = plan.kmv(V, diag_add=0.25, row_range=(100, 357))
+        assert rows.shape == (257, t) and rel(rows, ref[100:357]) < 1e-5
+        plan.set_operator(X, W, 2.0 / ell, None, c)                            # new hyper-parameters through the same buffers
+        Z2 = orc.scaled_projection(X, W, ell / 2.0, prescale=True)
+        assert rel(plan.kmv(V), orc.kmv(Z2, Z2, c, J, K, V)) < 1e-5
+    finally:
+        plan.close()

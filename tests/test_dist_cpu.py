@@ -111,6 +111,45 @@ def test_rectangular_product_row_partition_world2():
     mp.spawn(_rect_worker, args=(2, _free_port(), 301, 77), nprocs=2, join=True)      # 151 + 150 test rows
 
 
+def _probe_worker(rank, world, port, out_dir):
+    """ranks with DIFFERENT local RNG streams: the SLQ probes are drawn on rank 0 and broadcast, so the stochastic
+    log-determinant is identical on every rank; operands that differ between ranks are reported, not silently reduced"""
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    try:
+        from rpgp.gp import settings
+        from rpgp.lazy import AddedDiagLazyTensor, DenseLazyTensor
+        g = torch.Generator().manual_seed(3)
+        A = torch.randn(60, 60, dtype=torch.float64, generator=g)
+        Kmat = (A @ A.t() / 60).requires_grad_(True)
+        y = torch.randn(60, 1, dtype=torch.float64, generator=g)
+        noise = torch.tensor(0.5, dtype=torch.float64, requires_grad=True)
+        torch.manual_seed(100 + rank)                              # the local streams differ
+        with settings.max_cholesky_size(0), settings.cg_tolerance(1e-10), settings.max_cg_iterations(500):
+            iq, ld = AddedDiagLazyTensor(DenseLazyTensor(Kmat), noise).inv_quad_logdet(inv_quad_rhs=y, logdet=True)
+            (iq + ld).backward()
+        vals = torch.stack([iq.detach(), ld.detach(), noise.grad])
+        gathered = [torch.empty_like(vals) for _ in range(world)]
+        dist.all_gather(gathered, vals)
+        assert all(torch.equal(gathered[0], v) for v in gathered), gathered
+        rdist.assert_replicated("identical tensors", Kmat, y)
+        try:
+            rdist.assert_replicated("a rank-dependent tensor", y + rank)
+            raised = False
+        except RuntimeError as e:
+            raised = "differs between rank 0 and rank 1" in str(e)
+        assert raised
+        x = torch.full((4,), float(rank))
+        assert torch.equal(rdist.broadcast_(x), torch.zeros(4))
+    finally:
+        dist.destroy_process_group()
+
+
+def test_slq_probes_are_broadcast_and_replication_is_checked(tmp_path):
+    mp.spawn(_probe_worker, args=(2, _free_port(), str(tmp_path)), nprocs=2, join=True)
+
+
 def test_partition_arithmetic():
     p = rdist.Partition(10, 4, 3)
     assert (p.block, p.r0, p.r1) == (3, 9, 10)

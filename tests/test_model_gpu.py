@@ -28,9 +28,7 @@ GOLD = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden")
 DEV = torch.device("cuda:0")
 
 
-def rel(a, b):
-    a, b = np.asarray(a, dtype=np.float64), np.asarray(b, dtype=np.float64)
-    return np.linalg.norm(a - b) / max(np.linalg.norm(b), 1e-300)
+from parity_util import rel  # noqa: E402  (norm-wise error; its repr adds the row-wise / element-wise figures)
 
 
 # ---- golden vectors through the reference-facing classes ---------------------------------------------------------------

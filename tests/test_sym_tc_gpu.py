@@ -7,13 +7,10 @@ import torch
 from oracle import rpgp_oracle as orc
 from rpgp import _lib
 
+from parity_util import rel, sampled_oracle_check
+
 pytestmark = pytest.mark.gpu
 DEV = torch.device("cuda:0")
-
-
-def rel(a, b):
-    a, b = np.asarray(a, np.float64), np.asarray(b, np.float64)
-    return np.linalg.norm(a - b) / max(np.linalg.norm(b), 1e-300)
 
 
 def setup(n, J, t, seed, spread=1.0, K=1):
@@ -137,3 +134,66 @@ def test_tensor_core_distances_block_ranges_sum_to_full():
                 for b0, b1 in [(0, 4), (4, 9), (9, nb)])
     assert rel(parts, full) < 2e-6
     assert rel(full, orc.kmv(Z, Z, c, 20, 5, V)) < 1e-5
+
+
+# ---- at the benchmarked scale: sampled rows against the FP64 C oracle ---------------------------------------------
+def _large(n, J, K, t, seed, spread):
+    rng = np.random.RandomState(seed)
+    Z = (rng.randn(n, J * K) * spread / np.sqrt(K)).astype(np.float32)
+    c = (rng.rand(J) + 0.1).astype(np.float32)
+    V = rng.randn(n, t).astype(np.float32)
+    lay = _lib.plan_layout(J, K)
+    zp = _lib.pack_coords(torch.from_numpy(Z).to(DEV), lay)
+    nlc = _lib.pack_log2c(torch.from_numpy(c).to(DEV), lay)
+    return c, V, lay, zp, nlc
+
+
+@pytest.mark.parametrize("n,J,K,t,spread", [(200_000, 20, 1, 11, 2.0), (262_144 + 77, 26, 1, 16, 1.0), (200_000, 20, 5, 11, 2.0),
+                                            (200_000, 1, 20, 11, 2.0)])
+def test_sym_large_n_sampled_rows_match_f64_oracle(n, J, K, t, spread):
+    """n >= 200k: ~1600 row blocks, the row side folds > 1500 tile epochs into Kahan-compensated FP32, the column side adds them with
+    FP64 RED; both the direct-difference kernel (K = 1) and the distance-on-tensor-core kernel (K = 5, 20).  Norm-wise AND row-wise
+    1e-5 on 128 sampled rows (first / last / random runs) against oracle_kmv_f64 on the identical packed coordinates."""
+    c, V, lay, zp, nlc = _large(n, J, K, t, seed=n % 1000 + J + K, spread=spread)
+    got = _lib.mvm_sym(zp, lay, nlc, torch.from_numpy(V).to(DEV))
+    (norm_rel, row_rel, _), text = sampled_oracle_check(zp, lay, c, J, K, V, got)
+    assert norm_rel < 1e-5 and row_rel < 1e-5, text
+
+
+def test_sym_eight_uneven_rank_shares_sum_to_full():
+    """single-GPU emulation of the 8-rank split of the unique block pairs (uneven shares, one of them empty): the partial products
+    summed in FP64 equal the full product -- what the NCCL all-reduce of bench.py / rpgp.ops.kmv_partitioned computes"""
+    n, J, t = 20_000 + 55, 20, 11
+    c, V, lay, zp, nlc = _large(n, J, 1, t, seed=8, spread=1.5)
+    Vd = torch.from_numpy(V).to(DEV)
+    full = _lib.mvm_sym(zp, lay, nlc, Vd).double()
+    nb = (n + 127) // 128
+    cuts = [0, 3, 3, 40, 41, 77, 100, 140, nb]
+    parts = sum(_lib.mvm_sym(zp, lay, nlc, Vd, block_range=(cuts[r], cuts[r + 1])).double() for r in range(8))
+    e = rel(parts.cpu().numpy(), full.cpu().numpy())
+    assert e < 2e-6, repr(e)
+    (norm_rel, row_rel, _), text = sampled_oracle_check(zp, lay, c, J, 1, V, parts.float())
+    assert norm_rel < 1e-5 and row_rel < 1e-5, text
+
+
+@pytest.mark.parametrize("J,K", [(20, 5), (1, 20)])
+def test_tensor_core_distances_at_the_gate_boundary(J, K):
+    """tight clusters whose centred, scaled squared group norm sits just under the device-side gate (rms r2 <= 200): the
+    distance-on-tensor-core kernel runs (checked from the same statistics the pre-pass computes) and must still hold 1e-5"""
+    n, t = 3000, 11
+    Z, c, lay, zp, nlc = _two_clusters(n, J, K, 185.0, seed=21 + K)
+    plan = _lib.mvm_sym_distance_plan(lay)
+    assert plan is not None
+    zc = zp - zp.mean(dim=1, keepdim=True)
+    r2 = torch.stack([(zc[ch, :, g * lay.KP:g * lay.KP + K] ** 2).sum(-1) for ch in range(lay.nchunks) for g in range(lay.G)
+                      if ch * lay.G + g < J])
+    rms = float((r2.double() ** 2).mean().sqrt())
+    assert 150.0 < rms <= plan["bound"] and float(r2.max()) <= 10 * plan["bound"], (rms, float(r2.max()))   # inside the gate, near its edge
+    V = np.random.RandomState(5).randn(n, t).astype(np.float32)
+    V[:, 0] = 1.0
+    got = _lib.mvm_sym(zp, lay, nlc, torch.from_numpy(V).to(DEV)).cpu().numpy()
+    ref = orc.kmv(Z, Z, c, J, K, V)
+    e = rel(got, ref)
+    assert e < 1e-5, repr(e)
+    e0 = rel(got[:, :1], ref[:, :1])
+    assert e0 < 1e-5, repr(e0)
