@@ -156,17 +156,19 @@ def max_rhs(lay, backward=False):
     return int(load().rpgp_max_rhs(ctypes.byref(lay), int(bool(backward))))
 
 
-# ---- workspace cache: one growing buffer per device (borrowed by the library during a launch) -------------------------
+# ---- workspace cache: one growing buffer per (device, stream), borrowed by the library during a launch --------------------
+# (launches on different streams may overlap, so they must not share scratch memory)
 _workspaces = {}
 
 
 def _workspace(device, nbytes):
     if nbytes == 0:
         return None, 0
-    buf = _workspaces.get(device)
+    key = (device, torch.cuda.current_stream(device).cuda_stream)
+    buf = _workspaces.get(key)
     if buf is None or buf.numel() < nbytes:
         buf = torch.empty(int(nbytes * 1.25) + 256, dtype=torch.uint8, device=device)
-        _workspaces[device] = buf
+        _workspaces[key] = buf
     return buf, buf.numel()
 
 

@@ -25,6 +25,7 @@ class ExactGP(Module):
         self.likelihood = likelihood
         self._mean_cache = None
         self._love_root = None
+        self._cache_key = None
 
     def _apply(self, fn):
         if self.train_inputs is not None:
@@ -60,8 +61,19 @@ class ExactGP(Module):
         return self._predict(inputs[0])
 
     # ---- exact prediction ------------------------------------------------------------------------------------------------
+    def _prediction_cache_key(self):
+        """the prediction caches (K^-1 (y - mu), the train operator, the LOVE root) are valid for one state of the parameters:
+        every in-place change -- optimizer steps, load_state_dict, `initialize`, property setters -- bumps a tensor's `_version`
+        (edits through `.data` do not and are not detected)"""
+        return tuple((id(p), p._version) for p in self.parameters()) + (id(self.train_inputs[0]), id(self.train_targets))
+
     def _predict(self, x_test):
         x_train = self.train_inputs[0]
+        key = self._prediction_cache_key()
+        if key != self._cache_key:              # parameters changed while the model stayed in eval mode (ADVICE r1)
+            self._mean_cache = None
+            self._love_root = None
+            self._cache_key = key
         with torch.no_grad():
             prior = self.forward(x_train)
             if self._mean_cache is None:

@@ -265,8 +265,8 @@ def train_exact_gp(trainX, trainY, testX, testY, kind, model_kwargs, train_kwarg
     else:
         model, likelihood, mll = fresh()
 
+    # default warning filter, as the reference (training_routines.py:535): repeated warnings from one location are recorded once
     with warnings.catch_warnings(record=True) as w:
-        warnings.simplefilter("always")
         trained_epochs = train_to_convergence(model, trainX, trainY, optimizer=optimizer_, objective=mll, isloss=False,
                                               **train_kwargs)
 
@@ -286,7 +286,6 @@ def train_exact_gp(trainX, trainY, testX, testY, kind, model_kwargs, train_kwarg
                 train_outputs = model(trainX)
                 model_metrics["train_mse"] = mean_squared_error(train_outputs.mean, trainY)
             with warnings.catch_warnings(record=True) as w2:
-                warnings.simplefilter("always")
                 test_outputs = model(testX)
                 pred_mean = test_outputs.mean
             if not skip_posterior_variances:
