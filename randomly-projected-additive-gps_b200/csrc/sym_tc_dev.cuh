@@ -29,6 +29,17 @@ __device__ __forceinline__ void umma5(uint32_t d_tmem, uint64_t adesc, uint64_t 
         "}\n" ::"r"(d_tmem), "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate)
         : "memory");
 }
+// A operand in TENSOR MEMORY (lanes = rows of M = 128, one 32-bit column per k; k-step s of 8 at column 8 s): no shared-memory read
+// for A, ~35 clk per M128 N32 K8 MMA instead of ~63 (tools/umma_probe4.cu, profiles/umma_rate_r02.txt)
+__device__ __forceinline__ void umma5_ts(uint32_t d_tmem, uint32_t a_tmem, uint64_t bdesc, uint32_t idesc, uint32_t accumulate) {
+    asm volatile(
+        "{\n\t"
+        ".reg .pred p;\n\t"
+        "setp.ne.b32 p, %4, 0;\n\t"
+        "tcgen05.mma.cta_group::1.kind::tf32 [%0], [%1], %2, %3, p;\n\t"
+        "}\n" ::"r"(d_tmem), "r"(a_tmem), "l"(bdesc), "r"(idesc), "r"(accumulate)
+        : "memory");
+}
 __device__ __forceinline__ void umma5_commit(uint64_t* bar) {
     asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(bar)) : "memory");
 }

@@ -25,10 +25,14 @@
 // CTA (one per SM, 24 warps):
 //   * 16 arithmetic warps in two teams of eight that take the tiles in turn (team = tile parity = S buffer): one team's exponentials
 //     fill the XU pipe while the other waits for its exponents, loads them, or splits and stores its S tile;
-//   * 4 epilogue warps (TMEM lane quadrants) for the column side; lane 0 of one of them issues the bulk copies;
-//   * 4 warps whose lane 0 issues one stream of MMAs each (a UTCHMMA blocks its issuing warp ~100-150 clk,
-//     profiles/umma_microbench_r01.txt): S.V, S^T.V, and the distance MMAs of the first / second group of a batch.
-// TMEM: D1 (row side) 2 x 32 columns, D2 (column side) 2 x 32, D0 (exponents) 2 teams x 2 buffers x 2 groups x 32.
+//   * 4 epilogue warps (TMEM lane quadrants) for the column side;
+//   * 4 helper warps, one elected lane each (warp-uniform control flow: sym_tc_dev.cuh elect_one): the S-side MMAs (S.V then S^T.V of
+//     a tile), the bulk copies, and the distance MMAs of team 0's / team 1's tiles.  One distance issuer PER TEAM (round 2): with a
+//     single in-order stream a team whose buffers are full stalls the other team's exponents as well; the tensor pipe serialises the
+//     MMAs either way (40 clk per M128 N32 K8 MMA whatever the number of issuing warps, profiles/umma_rate_r02.txt).  The copy warp
+//     refills a B-image stage as soon as the tile's distance MMAs have completed (ZFREE, committed by the distance issuer), not when
+//     the whole tile is through.
+// TMEM: D1 (row side) 2 x 32 columns, D2 (column side) 2 x 32, D0 (exponents) 2 teams x 3 buffers x 2 groups x 32 = all 512 columns.
 #include <algorithm>
 #include <cstdlib>
 #include <cstring>
@@ -47,7 +51,11 @@ constexpr int D_F = 4;            // tiles accumulated in TMEM per row-side epoc
 constexpr int D_ZST = 3;          // B-image stages
 constexpr int D_AW = 16;          // arithmetic warps
 constexpr int D_FC = 4;            // right-hand-side columns folded per arithmetic thread (16 warps: 4 lane quadrants x 4 column parts)
-constexpr int D_NDI = 2;          // distance-MMA issuing warps (one per group of a batch)
+constexpr int D_NDI = 2;          // distance-MMA issuing warps (one per team)
+#ifndef TCD_NBUF
+#define TCD_NBUF 2
+#endif
+constexpr int D_NBUF = TCD_NBUF;  // D0 buffers (batches of two groups) per team
 constexpr int D_ISSUERS = 2 + D_NDI; // row side, column side, distances
 constexpr int D_THREADS = 32 * (D_AW + 4 + D_ISSUERS);
 #ifndef TCD_DIAG
@@ -63,27 +71,40 @@ constexpr float D_PAD = 16384.f;  // exponent of padding rows / groups: 2^-16384
 // shared-memory map (bytes from a 1024-aligned base)
 constexpr uint32_t D_S = 0;                    // S operand: buffer b at b*32768: tf32 part [128 rows][128 B], remainder 16384 B later
 constexpr uint32_t D_BC = 65536;               // B operand of the column side: V of this row block, 4 blocks x 4096 B
-constexpr uint32_t D_BT = 81920;               // B operand of the row side: V of the tile's columns, 2 stages x 4096 B
-constexpr uint32_t D_EPI = 90112;              // column-side epilogue exchange: 2 x [4 quadrants][16 rows][16] floats
-constexpr uint32_t D_AIMG = 98304;             // A operand of the distance MMAs: NL line sets x [tf32 part | remainder] x [128 rows][128 B]
-__host__ __device__ constexpr uint32_t d_bimg(int NL) { return D_AIMG + (uint32_t)NL * 32768u; }   // B operand: 3 stages x NL x [hi|lo] x [32][128 B]
+constexpr int D_BST = 4;                       // stages of the row-side B operand
+constexpr uint32_t D_BT = 81920;               // B operand of the row side: V of the tile's columns, D_BST stages x 4096 B
+constexpr uint32_t D_EPI = 98304;              // column-side epilogue exchange: 2 x [4 quadrants][16 rows][16] floats
+constexpr uint32_t D_BIMG = 106496;            // B operand of the distance MMAs: D_ZST stages x NL x [hi|lo] x [32][128 B]
+__host__ __device__ constexpr uint32_t d_bimg(int NL) { return D_BIMG; }
 __host__ __device__ constexpr uint32_t d_bar(int NL) { return d_bimg(NL) + (uint32_t)D_ZST * NL * 8192u; }
 __host__ __device__ constexpr uint32_t d_smem_bytes(int NL) { return d_bar(NL) + 512 + 1024; }
 
 // TMEM columns
-constexpr uint32_t D_TM_D1 = 0, D_TM_D2 = 64, D_TM_D0 = 128;      // 128 + 4 x 64 = 384 columns in use, 512 allocated
+// TMEM columns: D1 (row side) 2 x 32, D2 (column side) 2 x 32, the A operand of the distance MMAs (this row block's augmented
+// coordinates, written once per CTA by tcgen05.st: k-step s at 8 s, tf32 parts then remainders) 2 x 4 NL x 8 <= 128, D0 2 teams x D_NBUF x 64
+constexpr uint32_t D_TM_D1 = 0, D_TM_D2 = 64, D_TM_A = 128, D_TM_D0 = 256;
+static_assert(D_TM_D0 + 2 * D_NBUF * 64 <= 512, "TMEM columns");
 
-// barrier indices
+// barrier indices (32 x 8 bytes)
 constexpr int BD_ZFULL = 0;      // [3]  bulk copy of a B image -> distance issuers
-constexpr int BD_BFULL = 3;      // [2]  bulk copy -> row-side MMA issuer (B tile of V)
-constexpr int BD_SFULL = 5;      // [2]  the tile's team -> MMA issuers (count 8)
-constexpr int BD_TDONE = 7;      // [2]  tcgen05.commit of the three S issuers (count 3)
-constexpr int BD_EREAD = 9;      // [2]  epilogue warps have read D2 (count 4)
-constexpr int BD_D1EMPTY = 11;   // [2]  arithmetic warps have folded an epoch of D1 (count 16)
-constexpr int BD_BCFULL = 13;    // [1]  bulk copy of the column-side B operand
-constexpr int BD_AFULL = 14;     // [1]  bulk copy of the A image
-constexpr int BD_D0FULL = 16;    // [2 teams][2]  tcgen05.commit of every distance issuer for a batch of two groups (count D_NDI)
-constexpr int BD_D0FREE = 20;    // [2 teams][2]  the team's warps have read the batch (count 8)
+constexpr int BD_ZFREE = 3;      // [3]  tcgen05.commit of the tile's distance issuer: the B image has been consumed
+constexpr int BD_BFULL = 6;      // [4]  bulk copy -> S-side issuer (B tile of V)
+constexpr int BD_SFULL = 10;     // [2]  the tile's team -> S-side issuer (count 8)
+constexpr int BD_TDONE = 12;     // [2]  tcgen05.commit of the S-side issuer after a tile's row-side and column-side MMAs
+constexpr int BD_EREAD = 14;     // [2]  epilogue warps have read D2 (count 4)
+constexpr int BD_D1EMPTY = 16;   // [2]  arithmetic warps have folded an epoch of D1 (count 16)
+constexpr int BD_BCFULL = 18;    // [1]  bulk copy of the column-side B operand
+constexpr int BD_AFULL = 19;     // [1]  the A image is in tensor memory (count 4: the warps of rows 0..127)
+constexpr int BD_D0FULL = 20;    // [2 teams][D_NBUF]  tcgen05.commit of the team's distance issuer for a batch of two groups
+constexpr int BD_D0FREE = 20 + 2 * D_NBUF;   // [2 teams][D_NBUF]  the team's warps have read the batch (count 8)
+constexpr int BD_STAG = 31;      // [1]  team 0 is half-way through the exponentials of its tile (count 8): team 1 starts its tile then
+static_assert(BD_D0FREE + 2 * D_NBUF <= BD_STAG, "barrier block is 256 bytes");
+#ifndef TCD_STAGGER
+#define TCD_STAGGER 0            // (experiment, no gain) keep the two teams half a tile out of phase: one team's waits, TMEM loads, S stores and fences then run
+#endif                           // under the other's exponentials instead of both idling the XU pipe together (profiles/tcd_timeline_r02.txt)
+#ifndef TCD_FENCE_ISSUER
+#define TCD_FENCE_ISSUER 0       // 0: every arithmetic warp fences its S stores (generic -> async proxy) before SFULL; 1 (experiment,
+#endif                           // same speed, parity tests pass): one fence by the S-side issuer after it has acquired SFULL
 
 __device__ __forceinline__ void tmem5_ld4(uint32_t taddr, float* v) {
     uint32_t r[4];
@@ -178,20 +199,25 @@ __global__ void __maxnreg__(80) mvm_sym_tcd_kernel(const SymDArgs a) {
 
     if (tid == 0) {
 #pragma unroll
-        for (int s = 0; s < D_ZST; ++s) mbar_init(&bars[BD_ZFULL + s], 1);
+        for (int s = 0; s < D_ZST; ++s) {
+            mbar_init(&bars[BD_ZFULL + s], 1);
+            mbar_init(&bars[BD_ZFREE + s], 1);
+        }
+#pragma unroll
+        for (int s = 0; s < D_BST; ++s) mbar_init(&bars[BD_BFULL + s], 1);
 #pragma unroll
         for (int b = 0; b < 2; ++b) {
-            mbar_init(&bars[BD_BFULL + b], 1);
             mbar_init(&bars[BD_SFULL + b], D_AW / 2);
-            mbar_init(&bars[BD_TDONE + b], 2);
+            mbar_init(&bars[BD_TDONE + b], 1);
             mbar_init(&bars[BD_EREAD + b], 4);
             mbar_init(&bars[BD_D1EMPTY + b], D_AW);
         }
         mbar_init(&bars[BD_BCFULL], 1);
-        mbar_init(&bars[BD_AFULL], 1);
+        mbar_init(&bars[BD_AFULL], 4);
+        mbar_init(&bars[BD_STAG], D_AW / 2);
 #pragma unroll
-        for (int s = 0; s < 4; ++s) {
-            mbar_init(&bars[BD_D0FULL + s], D_NDI);
+        for (int s = 0; s < 2 * D_NBUF; ++s) {
+            mbar_init(&bars[BD_D0FULL + s], 1);
             mbar_init(&bars[BD_D0FREE + s], D_AW / 2);
         }
         mbar_fence_init();
@@ -219,6 +245,33 @@ __global__ void __maxnreg__(80) mvm_sym_tcd_kernel(const SymDArgs a) {
 #pragma unroll
         for (int q = 0; q < D_FC / 2; ++q) { acc[q] = 0ull; comp[q] = 0ull; }
 
+        // the A operand of the distance MMAs goes to tensor memory once per CTA: warps 0..3 (thread = row = TMEM lane) read their
+        // row's 128-byte lines of the pre-pass image (un-swizzling the 16-byte units) and tcgen05.st them, 32 columns at a time
+        if (warp < 4 && it.next_live(0) < it.ntiles) {
+            const unsigned char* arow = a.aimg + ((size_t)chunk * a.nblocks + it.I) * NL * 32768 + (size_t)rtid * 128;
+#pragma unroll
+            for (int lp = 0; lp < 2 * NL; ++lp) {      // lp = 2 * line + plane (tf32 part | remainder)
+                uint32_t v[32];
+#pragma unroll
+                for (int u = 0; u < 8; ++u) {
+                    const uint4 q = __ldg(reinterpret_cast<const uint4*>(arow + (size_t)lp * 16384 + (size_t)((u ^ (rtid & 7)) << 4)));
+                    v[4 * u] = q.x; v[4 * u + 1] = q.y; v[4 * u + 2] = q.z; v[4 * u + 3] = q.w;
+                }
+                const uint32_t ta = tmem + D_TM_A + (uint32_t)((lp & 1) * NL * 32 + (lp >> 1) * 32) + lanes;
+                asm volatile(
+                    "tcgen05.st.sync.aligned.32x32b.x32.b32 [%0], {%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15,%16,%17,%18,%19,%20,%21,%22,%23,%24,"
+                    "%25,%26,%27,%28,%29,%30,%31,%32};" ::"r"(ta),
+                    "r"(v[0]), "r"(v[1]), "r"(v[2]), "r"(v[3]), "r"(v[4]), "r"(v[5]), "r"(v[6]), "r"(v[7]), "r"(v[8]), "r"(v[9]), "r"(v[10]), "r"(v[11]),
+                    "r"(v[12]), "r"(v[13]), "r"(v[14]), "r"(v[15]), "r"(v[16]), "r"(v[17]), "r"(v[18]), "r"(v[19]), "r"(v[20]), "r"(v[21]), "r"(v[22]),
+                    "r"(v[23]), "r"(v[24]), "r"(v[25]), "r"(v[26]), "r"(v[27]), "r"(v[28]), "r"(v[29]), "r"(v[30]), "r"(v[31])
+                    : "memory");
+            }
+            asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory");
+            tc5_fence_before();
+            __syncwarp();
+            if (lane == 0) mbar5_arrive(&bars[BD_AFULL]);
+        }
+
         // every warp folds its rows' share (4 of the 16 right-hand sides) of a closed row-side epoch into the running total
         auto fold_epoch = [&](int e) {
             float d[D_FC], x[D_FC];
@@ -237,8 +290,8 @@ __global__ void __maxnreg__(80) mvm_sym_tcd_kernel(const SymDArgs a) {
             }
         };
 
-        // D0 is handed over in batches of two groups: the team's item i = (tile, batch) lives in the team's D0 buffer i & 1 and is
-        // released as soon as its exponents are in registers
+        // D0 is handed over in batches of two groups: the team's item i = (tile, batch) lives in the team's D0 buffer i % D_NBUF and
+        // is released as soon as its exponents are in registers
         uint32_t un[32];
         auto ld_group = [&](uint32_t col, int gb) {
             asm volatile(
@@ -261,26 +314,40 @@ __global__ void __maxnreg__(80) mvm_sym_tcd_kernel(const SymDArgs a) {
 #pragma unroll
         for (int q = 0; q < 32; ++q) un[q] = 0u;
         int j = 0, folded = 0;       // j counts the live tiles of BOTH teams
-        uint32_t item = 0;           // this team's (tile, batch) counter
+        uint32_t item = 0, ibuf = 0, iuse = 0;   // this team's (tile, batch) counter, item % D_NBUF, item / D_NBUF
         for (int t = it.next_live(0); t < it.ntiles; t = it.next_live(t + 1), ++j) {
             if ((j & 1) != team) continue;
             const int b = team;
             const long long c0 = it.col0(t) + half * 16;
             const bool diag = it.diag(t);
-            if (j >= 2) {   // tile j-2 has left the tensor core: S buffer b is free, and (the row issuer commits in tile order) every
-                            // epoch that ended at or before tile j-2 is closed
-                mbar_wait(&bars[BD_TDONE + b], (uint32_t)(((j >> 1) - 1) & 1));
-                tc5_fence_after();
-                while ((folded + 1) * D_F <= j - 1) fold_epoch(folded++);
-            }
-            if (tid == 0 || tid == 256) TCD_STAMP(j, 0);
+            if (tid == 0 || tid == 256) TCD_STAMP(j, 3);
+            if (TCD_STAGGER && team == 1) mbar_wait(&bars[BD_STAG], (uint32_t)((j >> 1) & 1));      // (team 0's tile j - 1)
             float s[16];
 #pragma unroll
             for (int c = 0; c < 16; ++c) s[c] = 0.f;
+            // exponentials of one group (16 columns of this thread's row) from register slot gb
+            auto exp_group = [&](int gb, int g) {
+                float u[16];
+#pragma unroll
+                for (int c = 0; c < 16; ++c) u[c] = __uint_as_float(un[16 * gb + c]);
+                if (diag) {     // a pair with itself: the exact exponent (no cancellation error on the dominant entries of K)
+                    const int jg = chunk * G + g;
+                    const float nl = jg < a.J ? __ldg(a.nlc + jg) : D_PAD;
+#pragma unroll
+                    for (int c = 0; c < 16; ++c)
+                        if (c0 + c == row) u[c] = nl;
+                }
+#pragma unroll
+                for (int c = 0; c < 16; ++c) s[c] += ex2_ftz(-u[c]);
+            };
+            // (tried in round 2 and not kept: issuing the tcgen05.ld of the next group under the exponentials of the current one --
+            // no gain, profiles/tcd_variants_r02.txt: with 16 free-running warps the loads already overlap the other warps' MUFU work)
             for (int k = 0; k < NB; ++k, ++item) {
                 const int g0 = 2 * k, gcnt = min(2, G - g0);
-                const uint32_t buf = (uint32_t)(2 * team) + (item & 1u);
-                mbar_wait(&bars[BD_D0FULL + buf], (item >> 1) & 1u);
+                const uint32_t buf = (uint32_t)(D_NBUF * team) + ibuf;
+                mbar_wait(&bars[BD_D0FULL + buf], iuse & 1u);
+                if (k == 0 && (tid == 0 || tid == 256)) TCD_STAMP(j, 4);
+                if (++ibuf == D_NBUF) { ibuf = 0; ++iuse; }
                 tc5_fence_after();
                 ld_group(64u * buf, 0);
                 if (gcnt > 1) ld_group(64u * buf, 1);
@@ -288,25 +355,22 @@ __global__ void __maxnreg__(80) mvm_sym_tcd_kernel(const SymDArgs a) {
                 tc5_fence_before();
                 __syncwarp();
                 if (lane == 0) mbar5_arrive(&bars[BD_D0FREE + buf]);
-#pragma unroll
-                for (int gb = 0; gb < 2; ++gb) {
-                    if (gb < gcnt) {
-                        float u[16];
-#pragma unroll
-                        for (int c = 0; c < 16; ++c) u[c] = __uint_as_float(un[16 * gb + c]);
-                        if (diag) {     // a pair with itself: the exact exponent (no cancellation error on the dominant entries of K)
-                            const int jg = chunk * G + g0 + gb;
-                            const float nl = jg < a.J ? __ldg(a.nlc + jg) : D_PAD;
-#pragma unroll
-                            for (int c = 0; c < 16; ++c)
-                                if (c0 + c == row) u[c] = nl;
-                        }
-#pragma unroll
-                        for (int c = 0; c < 16; ++c) s[c] += ex2_ftz(-u[c]);
-                    }
+                exp_group(0, g0);
+                if (gcnt > 1) exp_group(1, g0 + 1);
+                if (TCD_STAGGER && team == 0 && k == (NB - 1) / 2) {
+                    __syncwarp();
+                    if (lane == 0) mbar5_arrive(&bars[BD_STAG]);
                 }
             }
             if (tid == 0 || tid == 256) TCD_STAMP(j, 1);
+            if (j >= 2) {   // only now is the S buffer needed: tile j-2 has left the tensor core (its exponentials ran under the S-side
+                            // MMAs of the team's previous tile), and -- the S-side issuer commits in tile order -- every row-side epoch
+                            // that ended at or before tile j-2 is closed
+                mbar_wait(&bars[BD_TDONE + b], (uint32_t)(((j >> 1) - 1) & 1));
+                tc5_fence_after();
+                while ((folded + 1) * D_F <= j - 1) fold_epoch(folded++);
+            }
+            if (tid == 0 || tid == 256) TCD_STAMP(j, 0);
             // split, SWIZZLE_128B_BASE32B (32-byte chunks ^ row % 4), row-local stores (padding rows / columns hold exact zeros:
             // their exponent is >= D_PAD)
             unsigned char* sc = sm + D_S + (uint32_t)b * 32768u;
@@ -320,9 +384,9 @@ __global__ void __maxnreg__(80) mvm_sym_tcd_kernel(const SymDArgs a) {
                 *reinterpret_cast<float4*>(sc + off) = h;
                 *reinterpret_cast<float4*>(sc + 16384u + off) = l;
             }
-            fence5_async_smem();
+            if (!TCD_FENCE_ISSUER) fence5_async_smem();
             __syncwarp();
-            if (lane == 0) mbar5_arrive(&bars[BD_SFULL + b]);
+            if (lane == 0) mbar5_arrive(&bars[BD_SFULL + b]);      // (release: the S-side issuer acquires, then fences the proxies)
             if (tid == 0 || tid == 256) TCD_STAMP(j, 2);
         }
         if (j > 0) {    // j = number of live tiles; the row issuer's last commit covers every earlier row-side MMA (the last two
@@ -344,60 +408,15 @@ __global__ void __maxnreg__(80) mvm_sym_tcd_kernel(const SymDArgs a) {
             }
         }
     } else if (warp < D_AW + 4) {
-        // =========================================== epilogue warps (+ bulk copies) =====================================
+        // =========================================== epilogue warps (column side) ========================================
         const int qd = warp - D_AW;                                // TMEM lane quadrant
-        const bool loader = (qd == 1);      // the whole warp keeps the copy counters; one elected lane issues (elect_one: no waterfall loops)
-        const unsigned char* bsplit = reinterpret_cast<const unsigned char*>(a.bsplit);
-        const unsigned char* bimg = a.bimg + (size_t)chunk * a.nblocks * 4 * NL * 8192;
-
-        // the loader runs ahead of the consumers: B images three deep, B tiles of V two deep
-        int tz = it.next_live(0), jz = 0, tb = tz, jb = 0;
-        auto load_z = [&]() {
-            const long long c0 = it.col0(tz);
-            const int zs = jz % D_ZST;
-            if (elect_one()) {
-                mbar_expect_tx(&bars[BD_ZFULL + zs], (uint32_t)NL * 8192u);
-                bulk_g2s(sm + d_bimg(NL) + (uint32_t)zs * NL * 8192u, bimg + (size_t)(c0 / T5_BN) * NL * 8192, (uint32_t)NL * 8192u, &bars[BD_ZFULL + zs]);
-            }
-            __syncwarp();
-            tz = it.next_live(tz + 1);
-            ++jz;
-        };
-        auto load_b = [&]() {
-            const long long c0 = it.col0(tb);
-            const int bs = jb & 1;
-            if (elect_one()) {
-                mbar_expect_tx(&bars[BD_BFULL + bs], 4096u);
-                bulk_g2s(sm + D_BT + (uint32_t)bs * 4096u, bsplit + (c0 / T5_BN) * 4096, 4096u, &bars[BD_BFULL + bs]);
-            }
-            __syncwarp();
-            tb = it.next_live(tb + 1);
-            ++jb;
-        };
-        if (loader && tz < it.ntiles) {   // (a CTA without tiles must not leave copies in flight)
-            if (elect_one()) {
-                mbar_expect_tx(&bars[BD_AFULL], (uint32_t)NL * 32768u);
-                bulk_g2s(sm + D_AIMG, a.aimg + ((size_t)chunk * a.nblocks + it.I) * NL * 32768, (uint32_t)NL * 32768u, &bars[BD_AFULL]);
-                mbar_expect_tx(&bars[BD_BCFULL], 16384u);
-                bulk_g2s(sm + D_BC, bsplit + (long long)it.I * 16384, 16384u, &bars[BD_BCFULL]);
-            }
-            __syncwarp();
-            for (int s = 0; s < D_ZST && tz < it.ntiles; ++s) load_z();
-            for (int s = 0; s < 2 && tb < it.ntiles; ++s) load_b();
-        }
-        __syncwarp();
-
         int j = 0, jc = 0;
         for (int t = it.next_live(0); t < it.ntiles; t = it.next_live(t + 1), ++j) {
             const int b = j & 1;
             const bool diag = it.diag(t);
             mbar_wait_ns(a.sleep_ns, &bars[BD_TDONE + b], (uint32_t)((j >> 1) & 1));
             tc5_fence_after();
-            if (loader) {   // tile j is through: its B-image stage, S buffer and B stage are free
-                if (tz < it.ntiles) load_z();
-                if (tb < it.ntiles) load_b();
-            }
-            __syncwarp();
+            if (qd == 0 && lane == 0) TCD_STAMP(j, 7);
             // quadrants 0,1 hold the tf32-part rows of columns 0..15 / 16..31 (lanes 0..15), quadrants 2,3 the remainder rows
             float* P = reinterpret_cast<float*>(sm + D_EPI) + (jc & 1) * 1024;
             if (!diag) {
@@ -427,54 +446,45 @@ __global__ void __maxnreg__(80) mvm_sym_tcd_kernel(const SymDArgs a) {
                 }
                 ++jc;
             }
+            if (qd == 0 && lane == 0) TCD_STAMP(j, 8);
         }
     } else {
-        // =========================================== MMA issuers (lane 0 of one warp each) ==============================
-        // a UTCHMMA blocks its issuing warp ~150 clk whatever its size, so every stream of MMAs has a warp of its own and none of
-        // them does anything else: role 0 row side, roles 1/2 column side (tile rows 0..63 / 64..127), roles 3.. distances
+        // =========================================== helper warps =========================================================
+        // role 0: S-side MMAs (row side, then column side of every tile); role 1: bulk copies; roles 2, 3: distance MMAs of team 0 / 1.
+        // Every lane follows the barriers; tcgen05.mma / commit / cp.async.bulk are issued by one elected lane (elect_one).
         const int role = warp - D_AW - 4;
         const bool has_tiles = it.next_live(0) < it.ntiles;
-        // every lane of an issuing warp follows the barriers; the MMAs and their commit are issued under elect.sync (elect_one):
-        // warp-uniform control flow lets ptxas emit the UTCHMMAs back to back from uniform registers (sym_tc_dev.cuh)
         if (has_tiles && role == 0) {
             constexpr uint32_t IDESC_ROW_N32 = idesc5_tf32(128, 2 * T5_N, 0, 0), IDESC_ROW_N16 = idesc5_tf32(128, T5_N, 0, 0);
-            int j = 0;
-            for (int t = it.next_live(0); t < it.ntiles; t = it.next_live(t + 1), ++j) {   // D1 += Sh.[Vh|Vl] + Sl.Vh, four k-steps of 8 tile columns
-                const int b = j & 1, e = j / D_F;
-                mbar_wait_ns(a.sleep_ns, &bars[BD_BFULL + b], (uint32_t)((j >> 1) & 1));
-                if (j % D_F == 0 && e >= 2) mbar_wait_ns(a.sleep_ns, &bars[BD_D1EMPTY + (e & 1)], (uint32_t)(((e >> 1) - 1) & 1));
-                mbar_wait_ns(a.sleep_ns, &bars[BD_SFULL + b], (uint32_t)((j >> 1) & 1));
-                tc5_fence_after();
-                if (elect_one()) {
-                    const uint32_t sbuf = base + D_S + (uint32_t)b * 32768u;
-                    const uint32_t d1 = tmem + D_TM_D1 + 32u * (uint32_t)(e & 1);
-                    const uint64_t dA_h = smem_desc5(sbuf, 512, 512, LAYOUT5_SW128_BASE32B);
-                    const uint64_t dA_l = smem_desc5(sbuf + 16384u, 512, 512, LAYOUT5_SW128_BASE32B);
-                    const uint64_t dB = smem_desc5(base + D_BT + (uint32_t)b * 4096u, 16, 1024, LAYOUT5_SW128);
-#pragma unroll
-                    for (int ks = 0; ks < 4; ++ks) {
-                        if (TCD_DIAG & 4) break;
-                        umma5(d1, dA_h + (uint64_t)(ks * 2), dB + (uint64_t)(ks * 2), IDESC_ROW_N32, (j % D_F != 0 || ks > 0) ? 1u : 0u);
-                        umma5(d1, dA_l + (uint64_t)(ks * 2), dB + (uint64_t)(ks * 2), IDESC_ROW_N16, 1u);
-                    }
-                    umma5_commit(&bars[BD_TDONE + b]);
-                }
-                __syncwarp();
-            }
-        } else if (has_tiles && role == 1) {
             constexpr uint32_t IDESC_COL = idesc5_tf32(64, 2 * T5_N, 1, 0);
             mbar_wait_ns(a.sleep_ns, &bars[BD_BCFULL], 0u);
             int j = 0;
-            for (int t = it.next_live(0); t < it.ntiles; t = it.next_live(t + 1), ++j) {   // D2 = [Sh ; Sl]^T . [Vh|Vl], sixteen k-steps of 8 tile rows
-                const int b = j & 1;
+            for (int t = it.next_live(0); t < it.ntiles; t = it.next_live(t + 1), ++j) {
+                const int b = j & 1, e = j / D_F, bs = j % D_BST;
+                mbar_wait_ns(a.sleep_ns, &bars[BD_BFULL + bs], (uint32_t)((j / D_BST) & 1));
+                if (j % D_F == 0 && e >= 2) mbar_wait_ns(a.sleep_ns, &bars[BD_D1EMPTY + (e & 1)], (uint32_t)(((e >> 1) - 1) & 1));
                 if (j >= 2) mbar_wait_ns(a.sleep_ns, &bars[BD_EREAD + b], (uint32_t)(((j >> 1) - 1) & 1));        // D2[b] has been read
                 mbar_wait_ns(a.sleep_ns, &bars[BD_SFULL + b], (uint32_t)((j >> 1) & 1));
+                if (TCD_FENCE_ISSUER) fence5_async_smem();     // the team's S stores (acquired through SFULL) -> async proxy (tensor core)
                 tc5_fence_after();
-                const bool work = !it.diag(t) && !(TCD_DIAG & 2);      // (nothing to do on the diagonal block)
+                if (lane == 0) TCD_STAMP(j, 5);
+                const bool col_work = !it.diag(t) && !(TCD_DIAG & 2);      // (nothing to do for the column side on the diagonal block)
                 if (elect_one()) {
-                    if (work) {
+                    const uint32_t sbuf = base + D_S + (uint32_t)b * 32768u;
+                    if (!(TCD_DIAG & 4)) {      // D1 += Sh.[Vh|Vl] + Sl.Vh, four k-steps of 8 tile columns
+                        const uint32_t d1 = tmem + D_TM_D1 + 32u * (uint32_t)(e & 1);
+                        const uint64_t dA_h = smem_desc5(sbuf, 512, 512, LAYOUT5_SW128_BASE32B);
+                        const uint64_t dA_l = smem_desc5(sbuf + 16384u, 512, 512, LAYOUT5_SW128_BASE32B);
+                        const uint64_t dB = smem_desc5(base + D_BT + (uint32_t)bs * 4096u, 16, 1024, LAYOUT5_SW128);
+#pragma unroll
+                        for (int ks = 0; ks < 4; ++ks) {
+                            umma5(d1, dA_h + (uint64_t)(ks * 2), dB + (uint64_t)(ks * 2), IDESC_ROW_N32, (j % D_F != 0 || ks > 0) ? 1u : 0u);
+                            umma5(d1, dA_l + (uint64_t)(ks * 2), dB + (uint64_t)(ks * 2), IDESC_ROW_N16, 1u);
+                        }
+                    }
+                    if (col_work) {             // D2 = [Sh ; Sl]^T . [Vh|Vl], sixteen k-steps of 8 tile rows
                         const uint32_t d2 = tmem + D_TM_D2 + 32u * (uint32_t)b;
-                        const uint64_t dA = smem_desc5(base + D_S + (uint32_t)b * 32768u, 16384, 512, LAYOUT5_SW128_BASE32B);
+                        const uint64_t dA = smem_desc5(sbuf, 16384, 512, LAYOUT5_SW128_BASE32B);
                         const uint64_t dB = smem_desc5(base + D_BC, 16, 1024, LAYOUT5_SW128);
 #pragma unroll
                         for (int g = 0; g < 16; ++g)
@@ -483,47 +493,99 @@ __global__ void __maxnreg__(80) mvm_sym_tcd_kernel(const SymDArgs a) {
                     umma5_commit(&bars[BD_TDONE + b]);
                 }
                 __syncwarp();
+                if (lane == 0) TCD_STAMP(j, 6);
+            }
+        } else if (has_tiles && role == 1) {
+            // B images D_ZST deep (refilled at ZFREE of the tile that held the stage), B tiles of V D_BST deep (refilled at TDONE)
+            const unsigned char* bsplit = reinterpret_cast<const unsigned char*>(a.bsplit);
+            const unsigned char* bimg = a.bimg + (size_t)chunk * a.nblocks * 4 * NL * 8192;
+            int tz = it.next_live(0), jz = 0, tb = tz, jb = 0;
+            auto load_z = [&]() {
+                const long long c0 = it.col0(tz);
+                const int zs = jz % D_ZST;
+                if (elect_one()) {
+                    mbar_expect_tx(&bars[BD_ZFULL + zs], (uint32_t)NL * 8192u);
+                    bulk_g2s(sm + d_bimg(NL) + (uint32_t)zs * NL * 8192u, bimg + (size_t)(c0 / T5_BN) * NL * 8192, (uint32_t)NL * 8192u, &bars[BD_ZFULL + zs]);
+                }
+                __syncwarp();
+                tz = it.next_live(tz + 1);
+                ++jz;
+            };
+            auto load_b = [&]() {
+                const long long c0 = it.col0(tb);
+                const int bs = jb % D_BST;
+                if (elect_one()) {
+                    mbar_expect_tx(&bars[BD_BFULL + bs], 4096u);
+                    bulk_g2s(sm + D_BT + (uint32_t)bs * 4096u, bsplit + (c0 / T5_BN) * 4096, 4096u, &bars[BD_BFULL + bs]);
+                }
+                __syncwarp();
+                tb = it.next_live(tb + 1);
+                ++jb;
+            };
+            if (elect_one()) {
+                mbar_expect_tx(&bars[BD_BCFULL], 16384u);
+                bulk_g2s(sm + D_BC, bsplit + (long long)it.I * 16384, 16384u, &bars[BD_BCFULL]);
+            }
+            __syncwarp();
+            for (int s = 0; s < D_ZST && tz < it.ntiles; ++s) load_z();
+            for (int s = 0; s < D_BST && tb < it.ntiles; ++s) load_b();
+            // the stage of tile j's B image is free once its distance MMAs have completed (ZFREE), the stage of its V tile once the
+            // tile is through the S-side MMAs (TDONE); both barriers are followed in tile order
+            int j = 0;
+            for (int t = it.next_live(0); t < it.ntiles; t = it.next_live(t + 1), ++j) {
+                mbar_wait_ns(a.sleep_ns, &bars[BD_ZFREE + j % D_ZST], (uint32_t)((j / D_ZST) & 1));
+                if (tz < it.ntiles) load_z();
+                mbar_wait_ns(a.sleep_ns, &bars[BD_TDONE + (j & 1)], (uint32_t)((j >> 1) & 1));
+                if (tb < it.ntiles) load_b();
             }
         } else if (has_tiles && role - 2 < D_NDI) {
-            // issuer w owns the groups w, w + D_NDI, .. of every batch: U = Ah.Bh + Al.Bh + Ah.Bl into the batch's D0 columns, KS k-steps each
+            // issuer w owns team w's tiles (tile parity): U = Ah.Bh + Al.Bh + Ah.Bl for both groups of every batch into the batch's D0
+            // buffer, KS k-steps each.  It follows the B-image barriers of ALL tiles (a parity wait must not skip a phase).
             const int w = role - 2;
             constexpr uint32_t IDESC_D0 = idesc5_tf32(128, T5_BN, 0, 0);
             mbar_wait_ns(a.sleep_ns, &bars[BD_AFULL], 0u);
+            tc5_fence_after();
             int jd = 0;
-            uint32_t items[2] = {0u, 0u};      // per team: (tile, batch) counter
+            uint32_t ibuf = 0, iuse = 0;       // this team's (tile, batch) counter modulo / divided by D_NBUF
             for (int t = it.next_live(0); t < it.ntiles; t = it.next_live(t + 1), ++jd) {
-                const int zs = jd % D_ZST, team = jd & 1;
+                const int zs = jd % D_ZST;
                 mbar_wait_ns(a.sleep_ns, &bars[BD_ZFULL + zs], (uint32_t)((jd / D_ZST) & 1));
+                if ((jd & 1) != w) continue;
                 tc5_fence_after();
+                if (lane == 0) TCD_STAMP(jd, 9);
                 const uint32_t bst = base + d_bimg(NL) + (uint32_t)zs * NL * 8192u;
                 for (int k = 0; k < NB; ++k) {
-                    const uint32_t item = items[team]++;
-                    const int g = 2 * k + w;
-                    const uint32_t buf = (uint32_t)(2 * team) + (item & 1u), use = item >> 1;
-                    if (use >= 1) {
-                        mbar_wait_ns(a.sleep_ns, &bars[BD_D0FREE + buf], (use - 1) & 1u);
+                    const uint32_t buf = (uint32_t)(D_NBUF * w) + ibuf;
+                    if (iuse >= 1) {
+                        mbar_wait_ns(a.sleep_ns, &bars[BD_D0FREE + buf], (iuse - 1) & 1u);
                         tc5_fence_after();
                     }
                     if (elect_one()) {
-                        if (g < G) {
-                            const uint32_t d0 = tmem + D_TM_D0 + 64u * buf + 32u * (uint32_t)w;
-                            for (int ks = 0; ks < ((TCD_DIAG & 8) ? 0 : KS); ++ks) {
-                                const int ksi = g * KS + ks;
-                                const uint32_t l = (uint32_t)(ksi >> 2);
-                                const uint64_t o = (uint64_t)((ksi & 3) * 2);
-                                const uint64_t dAh = smem_desc5(base + D_AIMG + l * 32768u, 16, 1024, LAYOUT5_SW128) + o;
-                                const uint64_t dAl = smem_desc5(base + D_AIMG + l * 32768u + 16384u, 16, 1024, LAYOUT5_SW128) + o;
-                                const uint64_t dBh = smem_desc5(bst + l * 8192u, 16, 1024, LAYOUT5_SW128) + o;
-                                const uint64_t dBl = smem_desc5(bst + l * 8192u + 4096u, 16, 1024, LAYOUT5_SW128) + o;
-                                umma5(d0, dAh, dBh, IDESC_D0, ks > 0 ? 1u : 0u);
-                                umma5(d0, dAl, dBh, IDESC_D0, 1u);
-                                umma5(d0, dAh, dBl, IDESC_D0, 1u);
+#pragma unroll
+                        for (int gb = 0; gb < 2; ++gb) {
+                            const int g = 2 * k + gb;
+                            if (g < G) {
+                                const uint32_t d0 = tmem + D_TM_D0 + 64u * buf + 32u * (uint32_t)gb;
+                                for (int ks = 0; ks < ((TCD_DIAG & 8) ? 0 : KS); ++ks) {
+                                    const int ksi = g * KS + ks;
+                                    const uint32_t l = (uint32_t)(ksi >> 2);
+                                    const uint64_t o = (uint64_t)((ksi & 3) * 2);
+                                    const uint32_t aH = tmem + D_TM_A + 8u * (uint32_t)ksi, aL = aH + (uint32_t)(NL * 32);      // A from tensor memory
+                                    const uint64_t dBh = smem_desc5(bst + l * 8192u, 16, 1024, LAYOUT5_SW128) + o;
+                                    const uint64_t dBl = smem_desc5(bst + l * 8192u + 4096u, 16, 1024, LAYOUT5_SW128) + o;
+                                    umma5_ts(d0, aH, dBh, IDESC_D0, ks > 0 ? 1u : 0u);
+                                    umma5_ts(d0, aL, dBh, IDESC_D0, 1u);
+                                    umma5_ts(d0, aH, dBl, IDESC_D0, 1u);
+                                }
                             }
                         }
-                        umma5_commit(&bars[BD_D0FULL + buf]);      // (an issuer without a group in this batch still reports)
+                        umma5_commit(&bars[BD_D0FULL + buf]);
+                        if (k == NB - 1) umma5_commit(&bars[BD_ZFREE + zs]);     // the tile's B image has been consumed
                     }
                     __syncwarp();
+                    if (++ibuf == D_NBUF) { ibuf = 0; ++iuse; }
                 }
+                if (lane == 0) TCD_STAMP(jd, 10);
             }
         }
         __syncwarp();
@@ -754,11 +816,13 @@ int launch_sym_tcd(const float* zp, long long n, const Layout& lay, const float*
         RPGP_CUDA_OK(cudaStreamSynchronize(st));
         RPGP_CUDA_OK(cudaMemcpy(h, a.dbg, sizeof(h), cudaMemcpyDeviceToHost));
         cudaFree(a.dbg);
-        fprintf(stderr, "live tile: arithmetic start | exponentials done | SFULL   (clk since the first stamp; team = tile parity)\n");
-        for (int j = 0; j < 20; ++j) {
-            fprintf(stderr, "%2d:", j);
-            for (int k = 0; k < 3; ++k) fprintf(stderr, " %8lld", h[j * 12 + k] ? h[j * 12 + k] - h[0] : -1);
-            fprintf(stderr, "\n");
+        fprintf(stderr, "clk relative to tile 16's loop top; team = tile parity\n"
+                        "tile |  top  TDONEok D0FULL expdone SFULL | dist: Zfull issued | row: Sfull commit | col commit | epi: TDONE done\n");
+        const long long o = h[16 * 12 + 3];
+        for (int j = 16; j < 44; ++j) {
+            auto r = [&](int k) { return h[j * 12 + k] ? h[j * 12 + k] - o : -1; };
+            fprintf(stderr, "%3d  | %6lld %6lld %6lld %6lld %6lld | %6lld %6lld | %6lld %6lld | %6lld | %6lld %6lld\n", j, r(3), r(0), r(4), r(1), r(2), r(9), r(10), r(5),
+                    r(6), r(11), r(7), r(8));
         }
     }
 #endif

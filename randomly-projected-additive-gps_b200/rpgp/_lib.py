@@ -11,7 +11,7 @@ from ctypes import POINTER, Structure, c_char_p, c_double, c_float, c_int, c_int
 import torch
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "librpgp.so")
+LIB_PATH = os.environ.get("RPGP_LIB") or os.path.join(_HERE, "librpgp.so")     # RPGP_LIB: an experimental build (tools/build_variant.sh)
 
 LN2 = 0.6931471805599453
 

@@ -1,0 +1,15 @@
+#!/bin/bash
+# round 2, GPU call E: K > 1 kernel with the distance MMAs' A operand in tensor memory
+mkdir -p gpurun_out
+timeout 900 python -m pytest tests/test_sym_tc_gpu.py -x -q > gpurun_out/pytest_e.txt 2>&1
+echo "pytest rc=$?" >> gpurun_out/pytest_e.txt
+{
+for shape in "100000 20 5" "100000 1 20" "100000 8 6"; do
+  echo -n "variant=default "; timeout 120 python tools/tcd_check.py time $shape 2>&1 | tail -1
+done
+} > gpurun_out/times_e.txt 2>&1
+for shape in "100000 20 5" "100000 1 20"; do
+  echo "=== variant=stamps shape=$shape"
+  RPGP_LIB=$PWD/build/librpgp_stamps.so RPGP_TCD_DBG=1 timeout 120 python tools/tcd_check.py time $shape 2>&1 | tail -31
+done > gpurun_out/stamps_e.txt 2>&1
+tail -4 gpurun_out/pytest_e.txt; cat gpurun_out/times_e.txt; cat gpurun_out/stamps_e.txt
