@@ -58,8 +58,8 @@ typedef struct {
 
 /* base kernels k(d^2) of a projection group (training_routines.py:57-83 `_map_to_kernel`; gp_models/kernels/imq_kernel.py:8-9,47):
  *   RBF exp(-d^2/2);  Matern nu=1.5 (1 + sqrt3 d) exp(-sqrt3 d);  inverse multiquadric (d^2 + 1)^-1/2.
- * The non-RBF kernels run on the SIMT forward / gradient kernels with the group layouts (K = 1 is stored with KP = 2); the
- * symmetric tensor-core kernels are RBF only (rpgp_mvm_sym_supported returns 0). */
+ * The non-RBF kernels use the group layouts (K = 1 is stored with KP = 2) in the SIMT forward / gradient kernels and in the symmetric
+ * tensor-core kernel (round 2); only the distance-on-tensor-core variant of the latter is RBF (its exponent IS the squared distance). */
 typedef enum { RPGP_BASE_RBF = 0, RPGP_BASE_MATERN15 = 1, RPGP_BASE_INVERSE_MQ = 2 } rpgp_base_kernel;
 
 int rpgp_version(void);
@@ -86,6 +86,21 @@ int rpgp_pack_log2c_f32(const float* c, const rpgp_layout* lay, float* neg_log2c
  * or NULL (reciprocal lengthscales; prescale / postscale of scaled_projection_kernel.py:23-27). */
 int rpgp_project_f32(const float* X, int64_t n, int d, int64_t ldx, const float* W, const float* pre_inv,
                      const float* post_inv, const rpgp_layout* lay, float scale, float* Zp, void* stream);
+
+/* rpgp_project_f32 runs on the tensor cores (tcgen05 kind::tf32, 3xTF32 split, FP32 accumulation in tensor memory; csrc/project_tc.cu)
+ * when d <= 128 and J*K <= 112 (rpgp_project_tc_supported), otherwise on the FP64-accumulating SIMT kernel.
+ * rpgp_project2_f32: the same product with two optional outputs -- the packed planes Zp and / or the natural n x (J*K) matrix Zn (row
+ * stride ldz, NOT multiplied by `scale`), which is what the kernel classes' autograd graph carries.
+ * rpgp_project_bwd_f32: the vector-Jacobian product of the projection, dW[q][k] = sum_i dZ[i][q] X[i][k] (J*K x d, row-major): with
+ * Z[i][q] = post_inv[q] sum_k X[i][k] pre_inv[k] W[q][k] the gradients are dW = post_inv pre_inv^T * dW', d pre_inv[k] = sum_q post_inv[q]
+ * W[q][k] dW'[q][k], d post_inv[q] = sum_k pre_inv[k] W[q][k] dW'[q][k]  (what torch autograd derives from nn.Linear + div in
+ * scaled_projection_kernel.py:21-27).  Deterministic (per-CTA partials, FP64 reduction in a fixed order). */
+int rpgp_project_tc_supported(int d, const rpgp_layout* lay);
+int rpgp_project2_f32(const float* X, int64_t n, int d, int64_t ldx, const float* W, const float* pre_inv, const float* post_inv,
+                      const rpgp_layout* lay, float scale, float* Zp, float* Zn, int64_t ldz, void* stream);
+size_t rpgp_project_bwd_workspace_bytes(int64_t n, int d, int JK);
+int rpgp_project_bwd_f32(const float* X, int64_t n, int d, int64_t ldx, const float* dZ, int64_t ldz, int JK, float* dW, void* workspace,
+                         size_t workspace_bytes, void* stream);
 
 /* forward K.V ---------------------------------------------------------------------------------------------------- */
 size_t rpgp_mvm_workspace_bytes(int64_t m, int64_t n, const rpgp_layout* lay, int t);

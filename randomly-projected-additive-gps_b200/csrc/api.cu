@@ -108,8 +108,9 @@ int rpgp_plan_layout_base(int J, int K, int base, rpgp_layout* out) {
     for (const auto& s : shapes) {
         if (s[0] < K) continue;
         const int chunks = (J + s[1] - 1) / s[1];
-        // cost ~ FP32 lane-ops + MUFU-equivalent per (i,i') pair: chunks * (G*(KP+1) + 16)
-        const long long cost = (long long)chunks * (s[1] * (s[0] + 8) + 16);
+        // cost ~ FP32 lane-ops + MUFU-equivalent per (i,i') pair: chunks * (G*(KP+1) + 16); every chunk is also a full pass of the
+        // symmetric kernel's S.V / S^T.V products and of the right-hand sides (the +48)
+        const long long cost = (long long)chunks * (s[1] * (s[0] + 8) + 16 + 48);
         if (best_cost < 0 || cost < best_cost) {
             best_cost = cost;
             out->KP = s[0];
@@ -143,8 +144,34 @@ int rpgp_project_f32(const float* X, int64_t n, int d, int64_t ldx, const float*
     if (int rc = check_layout(lay)) return rc;
     RPGP_REQUIRE(n >= 0 && d >= 1 && ldx >= d, "project: n=%lld d=%d ldx=%lld", (long long)n, d, (long long)ldx);
     RPGP_REQUIRE(n == 0 || (X && W && Zp), "project: NULL pointer");
-    return launch_project(X, n, d, ldx, W, pre_inv, post_inv, *reinterpret_cast<const Layout*>(lay), scale, Zp,
+    return launch_project(X, n, d, ldx, W, pre_inv, post_inv, *reinterpret_cast<const Layout*>(lay), scale, Zp, nullptr, 0,
                           (cudaStream_t)stream);
+}
+
+int rpgp_project2_f32(const float* X, int64_t n, int d, int64_t ldx, const float* W, const float* pre_inv, const float* post_inv,
+                      const rpgp_layout* lay, float scale, float* Zp, float* Zn, int64_t ldz, void* stream) {
+    if (int rc = check_layout(lay)) return rc;
+    RPGP_REQUIRE(n >= 0 && d >= 1 && ldx >= d, "project2: n=%lld d=%d ldx=%lld", (long long)n, d, (long long)ldx);
+    RPGP_REQUIRE(n == 0 || (X && W && (Zp || Zn)), "project2: NULL pointer");
+    RPGP_REQUIRE(Zn == nullptr || ldz >= (int64_t)lay->J * lay->K, "project2: ldz=%lld < J*K", (long long)ldz);
+    return launch_project(X, n, d, ldx, W, pre_inv, post_inv, *reinterpret_cast<const Layout*>(lay), scale, Zp, Zn, ldz, (cudaStream_t)stream);
+}
+
+int rpgp_project_tc_supported(int d, const rpgp_layout* lay) {
+    return lay && check_layout(lay) == OK && project_tc_supported(d, *reinterpret_cast<const Layout*>(lay));
+}
+
+size_t rpgp_project_bwd_workspace_bytes(int64_t n, int d, int JK) {
+    if (n <= 0 || d <= 0 || JK <= 0) return 0;
+    return project_bwd_workspace_bytes(n, d, JK);
+}
+
+int rpgp_project_bwd_f32(const float* X, int64_t n, int d, int64_t ldx, const float* dZ, int64_t ldz, int JK, float* dW, void* workspace,
+                         size_t workspace_bytes, void* stream) {
+    RPGP_REQUIRE(n >= 0 && d >= 1 && JK >= 1 && ldx >= d && ldz >= JK, "project_bwd: n=%lld d=%d JK=%d ldx=%lld ldz=%lld", (long long)n, d, JK,
+                 (long long)ldx, (long long)ldz);
+    RPGP_REQUIRE(dW != nullptr && (n == 0 || (X && dZ)), "project_bwd: NULL pointer");
+    return launch_project_bwd(X, n, d, ldx, dZ, ldz, JK, dW, workspace, workspace_bytes, (cudaStream_t)stream);
 }
 
 size_t rpgp_mvm_workspace_bytes(int64_t m, int64_t n, const rpgp_layout* lay, int t) {
@@ -218,7 +245,7 @@ int rpgp_mvm_sym_distance_plan(const rpgp_layout* lay, int plan[5]) {
 }
 
 int rpgp_mvm_sym_supported(const rpgp_layout* lay, int t) {
-    return lay && check_layout(lay) == OK && lay->base == 0 && t >= 1 && t <= 16;     // the tensor-core kernels are RBF
+    return lay && check_layout(lay) == OK && t >= 1 && t <= 16;     // every base kernel (the distance-on-tensor-core variant is RBF only)
 }
 
 int rpgp_mvm_sym_f32(const float* zp, int64_t n, const rpgp_layout* lay, const float* neg_log2c, const float* Vp16, int t,

@@ -2,6 +2,8 @@
 // FP64 accumulation so the packed coordinate is a single rounding), dense rows of K, gradient reducers and the
 // un-tiled FP64 path.  See include/rpgp.h for the reference interfaces each one replaces.
 #include "rpgp_common.cuh"
+#include <cstdlib>
+
 #include "aux_kernels.cuh"
 
 namespace rpgp {
@@ -36,7 +38,7 @@ __global__ void pack_log2c_kernel(const float* __restrict__ c, Layout lay, float
 __global__ void __launch_bounds__(256) project_kernel(const float* __restrict__ X, long long n, int d, long long ldx,
                                                       const float* __restrict__ W, const float* __restrict__ pre_inv,
                                                       const float* __restrict__ post_inv, Layout lay, float scale,
-                                                      float* __restrict__ Zp, int w_in_smem) {
+                                                      float* __restrict__ Zp, float* __restrict__ Zn, long long ldz, int w_in_smem) {
     extern __shared__ double wsm[];  // [JK][d] (W * pre_inv)
     const int JK = lay.J * lay.K;
     if (w_in_smem) {
@@ -69,8 +71,9 @@ __global__ void __launch_bounds__(256) project_kernel(const float* __restrict__ 
             }
             if (post_inv) acc *= (double)post_inv[q];
             v = (float)(acc * (double)scale);
+            if (Zn) Zn[row * ldz + q] = (float)acc;
         }
-        Zp[((long long)chunk * n + row) * lay.CP + pos] = v;
+        if (Zp) Zp[((long long)chunk * n + row) * lay.CP + pos] = v;
     }
 }
 
@@ -240,8 +243,11 @@ int launch_pack_log2c(const float* c, const Layout& lay, float* nlc, cudaStream_
     return cuda_fail(cudaGetLastError(), "pack_log2c_kernel");
 }
 int launch_project(const float* X, long long n, int d, long long ldx, const float* W, const float* pre_inv,
-                   const float* post_inv, const Layout& lay, float scale, float* Zp, cudaStream_t st) {
+                   const float* post_inv, const Layout& lay, float scale, float* Zp, float* Zn, long long ldz, cudaStream_t st) {
     if (n == 0) return OK;
+    // tensor-core path (project_tc.cu) for d <= 128, J K <= 112; RPGP_PROJECT_TC=0 keeps everything on the FP64-accumulating SIMT kernel
+    static const int tc_env = [] { const char* e = getenv("RPGP_PROJECT_TC"); return e ? atoi(e) : 1; }();
+    if (tc_env && project_tc_supported(d, lay)) return launch_project_tc(X, n, d, ldx, W, pre_inv, post_inv, lay, scale, Zp, Zn, ldz, st);
     const size_t wbytes = (size_t)lay.J * lay.K * d * sizeof(double);
     const int in_smem = wbytes <= 200 * 1024;
     if (in_smem && wbytes > 48 * 1024) {
@@ -250,7 +256,7 @@ int launch_project(const float* X, long long n, int d, long long ldx, const floa
     }
     const long long nblocks = (n + 127) / 128;
     project_kernel<<<(unsigned)nblocks, 256, in_smem ? wbytes : 0, st>>>(X, n, d, ldx, W, pre_inv, post_inv, lay, scale,
-                                                                        Zp, in_smem);
+                                                                        Zp, Zn, ldz, in_smem);
     note_launch();
     return cuda_fail(cudaGetLastError(), "project_kernel");
 }

@@ -11,8 +11,17 @@ struct Layout {  // binary-compatible with rpgp_layout in include/rpgp.h
 
 int launch_pack_coords(const float* Z, long long n, long long ld, const Layout& lay, float scale, float* Zp, cudaStream_t st);
 int launch_pack_log2c(const float* c, const Layout& lay, float* nlc, cudaStream_t st);
+// Zp: packed planes (or NULL), Zn: natural n x J*K rows, row stride ldz, NOT multiplied by `scale` (or NULL)
 int launch_project(const float* X, long long n, int d, long long ldx, const float* W, const float* pre_inv,
-                   const float* post_inv, const Layout& lay, float scale, float* Zp, cudaStream_t st);
+                   const float* post_inv, const Layout& lay, float scale, float* Zp, float* Zn, long long ldz, cudaStream_t st);
+// project_tc.cu: the same on tcgen05 (3xTF32), and the vector-Jacobian product dW[q][k] = sum_i dZ[i][q] X[i][k]
+bool project_tc_supported(int d, const Layout& lay);
+int launch_project_tc(const float* X, long long n, int d, long long ldx, const float* W, const float* pre_inv, const float* post_inv,
+                      const Layout& lay, float scale, float* Zp, float* Zn, long long ldz, cudaStream_t st);
+bool project_bwd_supported(int d, int JK);
+size_t project_bwd_workspace_bytes(long long n, int d, int JK);
+int launch_project_bwd(const float* X, long long n, int d, long long ldx, const float* dZ, long long ldz, int JK, float* dW, void* ws,
+                       size_t ws_bytes, cudaStream_t st);
 int launch_rows_f32(const float* Zr, long long P, const float* Z2, long long n, long long ld, int J, int K, int base,
                     const float* c, float* out, long long ldo, cudaStream_t st);
 int launch_rows_f64(const double* Zr, long long P, const double* Z2, long long n, long long ld, int J, int K, int base,

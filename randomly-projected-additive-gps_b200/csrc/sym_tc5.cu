@@ -84,7 +84,7 @@ struct Sym5Args {
 
 }  // namespace
 
-template <int CP, int KP, int G, int NP2, int HALVES>
+template <int CP, int KP, int G, int NP2, int HALVES, int BASE = 0>
 __global__ void __launch_bounds__(128 * HALVES + 128, 2) mvm_sym_tc5_kernel(const Sym5Args a) {
     constexpr int GP = (KP == 1) ? CP : G;         // -log2c entries per chunk
     constexpr int AW = 4 * HALVES;                 // arithmetic warps
@@ -183,7 +183,7 @@ __global__ void __launch_bounds__(128 * HALVES + 128, 2) mvm_sym_tc5_kernel(cons
 #pragma unroll
                     for (int e = 0; e < 4; ++e) {
                         const int c = 4 * q + e;
-                        const float val = pair_kernel_value<CP, KP, G, NP2>(r, zt + c * CP);
+                        const float val = pair_kernel_value<CP, KP, G, NP2, BASE>(r, zt + c * CP);
                         sv[e] = (FULL || c < cols) ? val : 0.f;      // columns behind a partial tile hold stale bytes
                     }
                     // split, SWIZZLE_128B_BASE32B (32-byte chunks ^ row % 4), row-local stores
@@ -356,9 +356,9 @@ __global__ void __launch_bounds__(128 * HALVES + 128, 2) mvm_sym_tc5_kernel(cons
     }
 }
 
-template <int CP, int KP, int G, int NP2, int HALVES>
+template <int CP, int KP, int G, int NP2, int HALVES, int BASE = 0>
 static int run_sym5(const Sym5Args& a, dim3 grid, cudaStream_t st) {
-    auto kernel = mvm_sym_tc5_kernel<CP, KP, G, NP2, HALVES>;
+    auto kernel = mvm_sym_tc5_kernel<CP, KP, G, NP2, HALVES, BASE>;
     cudaError_t e = cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)T5_SMEM_BYTES);
     if (e != cudaSuccess) return cuda_fail(e, "cudaFuncSetAttribute(mvm_sym_tc5_kernel)");
     kernel<<<grid, 128 * HALVES + 128, T5_SMEM_BYTES, st>>>(a);
@@ -442,7 +442,7 @@ int launch_sym_tc5(const float* zp, long long n, const Layout& lay, const float*
         } else {
             // K > 1, squared distances on the tensor cores (sym_tcd.cu) while the coordinates are small enough for the cancellation
             // in |z|^2 + |z'|^2 - 2 z.z'; the direct-difference kernel below then returns at once (and the other way round)
-            if (plan_tcd(lay).supported && workspace_bytes >= base_bytes + tcd_workspace_bytes(n, lay)) {
+            if (lay.base == 0 && plan_tcd(lay).supported && workspace_bytes >= base_bytes + tcd_workspace_bytes(n, lay)) {
                 const unsigned* gate = nullptr;
                 if (int rcd = launch_sym_tcd(zp, n, lay, nlc, bsplit, acc, nblocks, rb_begin, nrb, (unsigned char*)workspace + base_bytes,
                                              workspace_bytes - base_bytes, &gate, st))
@@ -453,7 +453,12 @@ int launch_sym_tc5(const float* zp, long long n, const Layout& lay, const float*
                 a.gate_sum4_max = gb.sum4_max;
             }
             // K > 1: the (KP, G, CP) chunk shapes of dispatch.cuh; one MUFU per group, so no polynomial offload; two threads per row
-#define RPGP_SYM5_KN(KPv, Gv, CPv, TPv) if (KP == KPv && G == Gv && CP == CPv) rc = run_sym5<CPv, KPv, Gv, 0, 2>(a, grid, st);
+            // (Matern-1.5 and the inverse multiquadric: the same kernel with another function of the group's squared distance)
+#define RPGP_SYM5_KN(KPv, Gv, CPv, TPv)                                                                                \
+            if (KP == KPv && G == Gv && CP == CPv)                                                                     \
+                rc = lay.base == BASE_MATERN15 ? run_sym5<CPv, KPv, Gv, 0, 2, BASE_MATERN15>(a, grid, st)              \
+                     : lay.base == BASE_IMQ    ? run_sym5<CPv, KPv, Gv, 0, 2, BASE_IMQ>(a, grid, st)                   \
+                                               : run_sym5<CPv, KPv, Gv, 0, 2, 0>(a, grid, st);
             RPGP_KN_SHAPE_LIST(RPGP_SYM5_KN, 0)
 #undef RPGP_SYM5_KN
             if (rc == ERR_UNSUPPORTED) set_error("mvm_sym: no kernel for chunk shape KP=%d G=%d CP=%d", KP, G, CP);

@@ -713,7 +713,7 @@ TcdPlan plan_tcd(const Layout& lay) {
     std::memset(&p, 0, sizeof(p));
     static const int enabled = [] { const char* e = getenv("RPGP_SYM_TCD"); return e ? atoi(e) : 1; }();
     static const int kmin = [] { const char* e = getenv("RPGP_SYM_TCD_KMIN"); return e ? atoi(e) : 4; }();
-    if (!enabled || lay.K < kmin || lay.K > 24) return p;
+    if (!enabled || lay.base != 0 || lay.K < kmin || lay.K > 24) return p;      // (RBF only: the exponent IS the distance)
     p.KS = (lay.K + 5) / 6;       // six coordinates + their two partial norms per k-step of eight
     const int gmax = 8 / p.KS;
     p.nchunks = (lay.J + gmax - 1) / gmax;

@@ -15,6 +15,7 @@ from torch import nn
 import rp
 from gp_models.kernels.etc import _sample_from_range
 from rpgp import gp as gpytorch
+from rpgp import ops
 
 
 class Identity(nn.Module):
@@ -79,7 +80,12 @@ class GeneralizedProjectionKernel(gpytorch.kernels.Kernel):
         self.cache_proj = not learn_proj  # may be switched off by hand
 
     def _project(self, x):
-        """all projections of x at once: (n x d) -> (n x sum(component_degrees))"""
+        """all projections of x at once: (n x d) -> (n x sum(component_degrees)).  A plain nn.Linear on float32 CUDA inputs goes through
+        the library's tensor-core projection and its explicit vector-Jacobian product (rpgp.ops.project), the bias is added after."""
+        pm = self.projection_module
+        if isinstance(pm, torch.nn.Linear) and ops.can_project(x, pm.weight):
+            z = ops.project(x, pm.weight)
+            return z if pm.bias is None else z + pm.bias
         return self.projection_module(x)
 
     def forward(self, x1, x2, **params):

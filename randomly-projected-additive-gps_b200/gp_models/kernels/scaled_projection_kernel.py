@@ -9,6 +9,7 @@ sm_100a kernel launch.
 import torch
 
 from rpgp import gp as gpytorch
+from rpgp import ops
 
 
 class ScaledProjectionKernel(gpytorch.kernels.Kernel):
@@ -26,6 +27,12 @@ class ScaledProjectionKernel(gpytorch.kernels.Kernel):
         self.prescale = prescale
 
     def _scaled_projection(self, x):
+        # float32 CUDA inputs through a bias-free nn.Linear take ONE library call (rpgp_project2_f32: tcgen05, 3xTF32) with an explicit
+        # vector-Jacobian product for l and W (rpgp_project_bwd_f32) instead of a cuBLAS GEMM + element-wise kernels + autograd
+        pm = self.projection_module
+        if isinstance(pm, torch.nn.Linear) and pm.bias is None and ops.can_project(x, pm.weight):
+            inv = self.lengthscale.reciprocal()
+            return ops.project(x, pm.weight, inv, None) if self.prescale else ops.project(x, pm.weight, None, inv)
         if self.prescale:
             return self.projection_module(x.div(self.lengthscale))
         return self.projection_module(x).div(self.lengthscale)

@@ -41,6 +41,12 @@ SIGNATURES = {
     "rpgp_pack_log2c_f32": (c_int, [c_void_p, POINTER(Layout), c_void_p, c_void_p]),
     "rpgp_project_f32": (c_int, [c_void_p, c_int64, c_int, c_int64, c_void_p, c_void_p, c_void_p, POINTER(Layout),
                                  c_float, c_void_p, c_void_p]),
+    "rpgp_project_tc_supported": (c_int, [c_int, POINTER(Layout)]),
+    "rpgp_project2_f32": (c_int, [c_void_p, c_int64, c_int, c_int64, c_void_p, c_void_p, c_void_p, POINTER(Layout),
+                                  c_float, c_void_p, c_void_p, c_int64, c_void_p]),
+    "rpgp_project_bwd_workspace_bytes": (c_size_t, [c_int64, c_int, c_int]),
+    "rpgp_project_bwd_f32": (c_int, [c_void_p, c_int64, c_int, c_int64, c_void_p, c_int64, c_int, c_void_p, c_void_p, c_size_t,
+                                     c_void_p]),
     "rpgp_mvm_workspace_bytes": (c_size_t, [c_int64, c_int64, POINTER(Layout), c_int]),
     "rpgp_mvm_fwd_f32": (c_int, [c_void_p, c_int64, c_int64, c_void_p, c_int64, c_int64, POINTER(Layout), c_void_p,
                                  c_void_p, c_int, c_void_p, c_int, c_void_p, c_size_t, c_void_p]),
@@ -258,6 +264,46 @@ def project(X, W, pre_inv, post_inv, lay, scale=None):
         _check(load().rpgp_project_f32(_ptr(X), n, d, X.stride(0), _ptr(W), _ptr(pre), _ptr(post), ctypes.byref(lay),
                                        coord_scale() if scale is None else float(scale), _ptr(out),
                                        _stream(X.device)), "rpgp_project_f32")
+    return out
+
+
+def project_tc_supported(d, lay):
+    return bool(load().rpgp_project_tc_supported(int(d), ctypes.byref(lay)))
+
+
+def project2(X, W, pre_inv, post_inv, lay, packed=True, natural=True, scale=None):
+    """The projection with both outputs (rpgp_project2_f32): (packed planes or None, natural n x J*K float32 or None)."""
+    require_cuda(X, W, pre_inv, post_inv)
+    assert X.dtype == torch.float32 and X.dim() == 2 and X.stride(1) == 1
+    W = W.contiguous().float()
+    n, d = X.shape
+    JK = lay.J * lay.K
+    assert W.shape == (JK, d)
+    zp = torch.empty((lay.nchunks, n, lay.CP), dtype=torch.float32, device=X.device) if packed else None
+    zn = torch.empty((n, JK), dtype=torch.float32, device=X.device) if natural else None
+    pre = None if pre_inv is None else pre_inv.reshape(-1).contiguous().float()
+    post = None if post_inv is None else post_inv.reshape(-1).contiguous().float()
+    with torch.cuda.device(X.device), _timed("project"):
+        _check(load().rpgp_project2_f32(_ptr(X), n, d, X.stride(0), _ptr(W), _ptr(pre), _ptr(post), ctypes.byref(lay),
+                                        coord_scale() if scale is None else float(scale), _ptr(zp), _ptr(zn), JK,
+                                        _stream(X.device)), "rpgp_project2_f32")
+    return zp, zn
+
+
+def project_bwd(X, dZ):
+    """dW'[q, k] = sum_i dZ[i, q] X[i, k]  (J*K x d): the vector-Jacobian product of the projection (rpgp_project_bwd_f32)."""
+    require_cuda(X, dZ)
+    assert X.dtype == torch.float32 and dZ.dtype == torch.float32 and X.dim() == 2 and dZ.dim() == 2
+    assert X.stride(1) == 1 and X.shape[0] == dZ.shape[0]
+    dZ = dZ if dZ.stride(1) == 1 else dZ.contiguous()
+    n, d = X.shape
+    JK = dZ.shape[1]
+    lib = load()
+    out = torch.empty((JK, d), dtype=torch.float32, device=X.device)
+    with torch.cuda.device(X.device), _timed("project_bwd"):
+        ws, ws_bytes = _workspace(X.device, lib.rpgp_project_bwd_workspace_bytes(n, d, JK))
+        _check(lib.rpgp_project_bwd_f32(_ptr(X), n, d, X.stride(0), _ptr(dZ), dZ.stride(0), JK, _ptr(out), _ptr(ws), ws_bytes,
+                                        _stream(X.device)), "rpgp_project_bwd_f32")
     return out
 
 

@@ -212,6 +212,62 @@ def kdense(Z1, Z2, c, J, K, base=0):
 
 
 # ----------------------------------------------------------------------------------------------------------------------
+# the projection Z = ((x * pre_inv) W^T) * post_inv as one library call with an explicit vector-Jacobian product
+# ----------------------------------------------------------------------------------------------------------------------
+class _Project(torch.autograd.Function):
+    """Z[i, q] = post_inv[q] * sum_k x[i, k] * pre_inv[k] * W[q, k]  (scaled_projection_kernel.py:21-27: prescale = pre_inv = 1 / l over
+    the d inputs, postscale = post_inv = 1 / l over the J*K outputs).  Forward: rpgp_project2_f32 (tcgen05, 3xTF32); backward:
+    rpgp_project_bwd_f32 gives dW' = dZ^T x, from which the gradients of W, pre_inv and post_inv are element-wise products of
+    (J*K x d) matrices; the gradient with respect to x (never needed by the training path) is a dense product."""
+
+    @staticmethod
+    def forward(ctx, x, W, pre_inv, post_inv):
+        JK, d = W.shape
+        lay = _lib.plan_layout(JK, 1)          # only the natural output is produced here: any layout of the right width will do
+        _, Z = _lib.project2(x.detach(), W.detach(), None if pre_inv is None else pre_inv.detach(),
+                             None if post_inv is None else post_inv.detach(), lay, packed=False, natural=True)
+        ctx.save_for_backward(x, W, pre_inv, post_inv)
+        return Z
+
+    @staticmethod
+    def backward(ctx, gZ):
+        x, W, pre_inv, post_inv = ctx.saved_tensors
+        gx = gW = gpre = gpost = None
+        need_w = ctx.needs_input_grad[1] or (pre_inv is not None and ctx.needs_input_grad[2]) or \
+            (post_inv is not None and ctx.needs_input_grad[3])
+        pre = None if pre_inv is None else pre_inv.reshape(1, -1)
+        post = None if post_inv is None else post_inv.reshape(-1, 1)
+        if need_w:
+            dWp = _lib.project_bwd(x.detach(), gZ.contiguous().float())           # (JK x d) = dZ^T x
+            Wd = W.detach()
+            if ctx.needs_input_grad[1]:
+                gW = dWp if pre is None else dWp * pre
+                gW = gW if post is None else gW * post
+            if pre_inv is not None and ctx.needs_input_grad[2]:
+                t = dWp * Wd
+                gpre = (t if post is None else t * post).sum(0).reshape(pre_inv.shape)
+            if post_inv is not None and ctx.needs_input_grad[3]:
+                t = dWp * Wd
+                gpost = (t if pre is None else t * pre).sum(1).reshape(post_inv.shape)
+        if ctx.needs_input_grad[0]:
+            Weff = W.detach()
+            Weff = Weff if pre is None else Weff * pre
+            Weff = Weff if post is None else Weff * post
+            gx = gZ @ Weff
+        return gx, gW, gpre, gpost
+
+
+def project(x, W, pre_inv=None, post_inv=None):
+    """Differentiable projection through the C ABI (float32 CUDA, 2-D); see _Project."""
+    return _Project.apply(x, W, pre_inv, post_inv)
+
+
+def can_project(x, W):
+    return (x.is_cuda and x.dtype == torch.float32 and x.dim() == 2 and x.stride(-1) == 1 and W.dtype == torch.float32
+            and W.dim() == 2 and x.shape[0] > 0)
+
+
+# ----------------------------------------------------------------------------------------------------------------------
 # row-partitioned products (multi-GPU): each rank computes its row block, NCCL all-gather rebuilds the product
 # ----------------------------------------------------------------------------------------------------------------------
 def kmv_partitioned(Z, c, J, K, V, packed=None, nlc=None, base=0):

@@ -47,6 +47,28 @@ def test_forward_and_rows_match_oracle(base, m, n, J, K, t):
     assert rel(rows64, orc.additive_rbf_dense(Z1[:9], Z2, c, J, K, base=base)) < 1e-12
 
 
+@pytest.mark.parametrize("base", [1, 2])
+@pytest.mark.parametrize("n,J,K,t", [(2000, 20, 1, 11), (1500, 26, 1, 16), (1300, 7, 3, 4), (1100, 1, 20, 11), (2500, 20, 5, 3), (1025, 40, 1, 1)])
+def test_symmetric_tensor_core_kernel_with_other_base_kernels(base, n, J, K, t):
+    """square products of n >= 1024 rows go to the symmetric tcgen05 kernel for every base kernel (round 2): against the oracle (1e-5)
+    and against the SIMT forward kernel on the same packed operands"""
+    from rpgp import _lib
+    Z, _, c, V = data(n, 3, J, K, t, seed=n + J + K + base)
+    d = lambda a: torch.from_numpy(a).to(DEV)      # noqa: E731
+    lay = _lib.plan_layout(J, K, base)
+    assert _lib.mvm_sym_supported(lay, t)
+    zp = _lib.pack_coords(d(Z), lay)
+    nlc = _lib.pack_log2c(d(c), lay)
+    got = _lib.mvm_sym(zp, lay, nlc, d(V)).cpu().numpy()
+    ref = orc.kmv(Z, Z, c, J, K, V, base=base)
+    assert rel(got, ref) < 1e-5, rel(got, ref)
+    simt = _lib.mvm_fwd(zp, zp, lay, nlc, d(V)).cpu().numpy()
+    assert rel(got, simt) < 3e-6, rel(got, simt)
+    zt = d(Z)
+    via_ops = ops.kmv_raw(zt, zt, d(c), J, K, d(V), base=base).cpu().numpy()              # the route the lazy operator takes
+    assert rel(via_ops, ref) < 1e-5
+
+
 def test_inverse_multiquadric_rows_match_reference_fixture():
     """dense rows of base kernel 2 against tests/golden/imq.npz (the reference's own postprocess_inverse_mq, imq_kernel.py:8-9)"""
     import os

@@ -44,6 +44,10 @@ def base_kernels(n=100_000, J=20, t=11):
         ms = timed(lambda: _lib.mvm_fwd(p.zp, p.zp, p.lay, nlc, V))
         print(json.dumps({"row": "f4", "what": "forward K.V, SIMT kernel, base=%s" % name, "n": n, "J": J, "t": t, "KP": p.lay.KP,
                           "ms": ms, "pair_evals_per_s": n * n * J / (ms * 1e-3)}), flush=True)
+        if _lib.mvm_sym_supported(p.lay, t):
+            ms = timed(lambda: _lib.mvm_sym(p.zp, p.lay, nlc, V))
+            print(json.dumps({"row": "f4", "what": "symmetric tcgen05 kernel, base=%s" % name, "n": n, "J": J, "t": t, "KP": p.lay.KP,
+                              "G": p.lay.G, "nchunks": p.lay.nchunks, "ms": ms, "pair_evals_per_s": n * n * J / (ms * 1e-3)}), flush=True)
 
 
 def predictive(n=50_000, nt=4096, J=20, rank=20):
@@ -83,7 +87,8 @@ def predictive(n=50_000, nt=4096, J=20, rank=20):
 
 
 if __name__ == "__main__":
-    for part in (base_kernels, predictive):
+    import sys
+    for part in ((base_kernels,) if "base" in sys.argv[1:] else (base_kernels, predictive)):
         try:
             part()
         except Exception as e:  # keep whatever was measured
