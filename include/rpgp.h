@@ -58,8 +58,9 @@ typedef struct {
 
 /* base kernels k(d^2) of a projection group (training_routines.py:57-83 `_map_to_kernel`; gp_models/kernels/imq_kernel.py:8-9,47):
  *   RBF exp(-d^2/2);  Matern nu=1.5 (1 + sqrt3 d) exp(-sqrt3 d);  inverse multiquadric (d^2 + 1)^-1/2.
- * The non-RBF kernels use the group layouts (K = 1 is stored with KP = 2) in the SIMT forward / gradient kernels and in the symmetric
- * tensor-core kernel (round 2); only the distance-on-tensor-core variant of the latter is RBF (its exponent IS the squared distance). */
+ * Every base kernel runs in the SIMT forward / gradient kernels and in the symmetric tensor-core kernel with the same layouts (K = 1:
+ * one coordinate and one MUFU per projection -- the distance is |d|, no square root); only the distance-on-tensor-core variant of the
+ * symmetric kernel is RBF (its exponent IS the squared distance).  Non-RBF kernels take right-hand-side widths 4 and 16 only. */
 typedef enum { RPGP_BASE_RBF = 0, RPGP_BASE_MATERN15 = 1, RPGP_BASE_INVERSE_MQ = 2 } rpgp_base_kernel;
 
 int rpgp_version(void);

@@ -48,11 +48,7 @@ static int check_layout(const rpgp_layout* lay) {
     RPGP_REQUIRE(lay->KP >= lay->K && lay->G * lay->KP <= lay->CP, "layout: group shape KP=%d G=%d exceeds CP=%d", lay->KP, lay->G, lay->CP);
     RPGP_REQUIRE((long long)lay->nchunks * lay->G >= lay->J, "layout: %d chunks x %d groups < J=%d", lay->nchunks, lay->G, lay->J);
     RPGP_REQUIRE(lay->base >= 0 && lay->base <= 2, "layout: base kernel %d (0 RBF, 1 Matern-1.5, 2 inverse multiquadric)", lay->base);
-    if (lay->base == 0) {
-        RPGP_REQUIRE((lay->K == 1) == (lay->KP == 1), "layout: KP must be 1 exactly when K is 1");
-    } else {
-        RPGP_REQUIRE(lay->KP >= 2, "layout: non-RBF base kernels use the group layouts (KP >= 2)");
-    }
+    RPGP_REQUIRE((lay->K == 1) == (lay->KP == 1), "layout: KP must be 1 exactly when K is 1");
     RPGP_REQUIRE(lay->KP > 1 || lay->G == lay->CP, "layout: K=1 requires G == CP");
     return OK;
 }
@@ -73,7 +69,7 @@ unsigned long long rpgp_launch_count(void) { return rpgp::launch_count(); }
 // TP actually compiled for (layout, t): forward K=1 {4,8,12,16,32}; backward K=1 {4,12,16}; K>1 {4,16}
 int rpgp_padded_rhs(const rpgp_layout* lay, int t, int backward) {
     if (!lay || t <= 0) return 0;
-    if (lay->KP > 1) return t <= 4 ? 4 : (t <= 16 ? 16 : 0);
+    if (lay->KP > 1 || lay->base != 0) return t <= 4 ? 4 : (t <= 16 ? 16 : 0);
     if (backward) return t <= 4 ? 4 : (t <= 12 ? 12 : (t <= 16 ? 16 : 0));
     if (t <= 4) return 4;
     if (t <= 8) return 8;
@@ -82,7 +78,7 @@ int rpgp_padded_rhs(const rpgp_layout* lay, int t, int backward) {
     if (t <= 32) return 32;
     return 0;
 }
-int rpgp_max_rhs(const rpgp_layout* lay, int backward) { return (lay && lay->KP == 1 && !backward) ? 32 : 16; }
+int rpgp_max_rhs(const rpgp_layout* lay, int backward) { return (lay && lay->KP == 1 && lay->base == 0 && !backward) ? 32 : 16; }
 
 int rpgp_plan_layout(int J, int K, rpgp_layout* out) { return rpgp_plan_layout_base(J, K, 0, out); }
 
@@ -93,7 +89,7 @@ int rpgp_plan_layout_base(int J, int K, int base, rpgp_layout* out) {
     out->J = J;
     out->K = K;
     out->base = base;
-    if (K == 1 && base == 0) {
+    if (K == 1) {      // one coordinate per projection, every base kernel (round 2: the non-RBF kernels used to be padded to KP = 2)
         out->KP = 1;
         out->nchunks = (J + 31) / 32;
         const int per = (J + out->nchunks - 1) / out->nchunks;
@@ -220,9 +216,10 @@ int rpgp_mvm_fwd_f32(const float* z1p, int64_t m, int64_t z1_stride, const float
     dim3 grid((unsigned)sp.row_blocks, (unsigned)sp.nsplits, (unsigned)lay->nchunks);
     // RPGP_POLY_PAIRS overrides the number of projection pairs evaluated on the FMA pipe (tools/poly_sweep.py); -1 = default
     static const int poly_env = [] { const char* e = getenv("RPGP_POLY_PAIRS"); return e ? atoi(e) : -1; }();
-    const int poly_pairs = (lay->KP == 1) ? (poly_env >= 0 ? poly_env : default_poly_pairs(lay->CP, TP)) : 0;
+    const int poly_pairs = (lay->KP == 1 && lay->base == 0) ? (poly_env >= 0 ? poly_env : default_poly_pairs(lay->CP, TP)) : 0;
     int rc;
-    if (lay->KP == 1 && poly_pairs > 0) rc = launch_fwd_k1_poly(lay->CP, TP, poly_pairs, a, grid, st);
+    if (lay->KP == 1 && lay->base != 0) rc = launch_fwd_k1_base(lay->CP, TP, lay->base, a, grid, st);
+    else if (lay->KP == 1 && poly_pairs > 0) rc = launch_fwd_k1_poly(lay->CP, TP, poly_pairs, a, grid, st);
     else rc = (lay->KP == 1) ? launch_fwd_k1(lay->CP, TP, a, grid, st) : launch_fwd_kn(lay->KP, lay->G, lay->CP, TP, lay->base, a, grid, st);
     if (rc) return rc;
     if (!a.direct) return launch_reduce_partials(a.partial, (int)nparts, m, TP, t, out, ldo, st);
@@ -305,7 +302,9 @@ int rpgp_quad_bwd_f32(const float* z1p, int64_t m, int64_t z1_stride, const floa
     a.m = m; a.n = n; a.z1_chunk_stride = z1_stride; a.z2_chunk_stride = z2_stride;
     a.cols_per_split = sp.cols_per_split; a.nsplits = sp.nsplits; a.nchunks = lay->nchunks; a.symmetric = symmetric ? 1 : 0;
     dim3 grid((unsigned)sp.row_blocks, (unsigned)sp.nsplits, (unsigned)lay->nchunks);
-    int rc = (lay->KP == 1) ? launch_grad_k1(lay->CP, TPk, a, grid, st) : launch_grad_kn(lay->KP, lay->G, lay->CP, TPk, lay->base, a, grid, st);
+    int rc = (lay->KP == 1 && lay->base != 0) ? launch_grad_k1_base(lay->CP, TPk, lay->base, a, grid, st)
+             : (lay->KP == 1)                 ? launch_grad_k1(lay->CP, TPk, a, grid, st)
+                                              : launch_grad_kn(lay->KP, lay->G, lay->CP, TPk, lay->base, a, grid, st);
     if (rc) return rc;
     // d k / d z1 = k * ln2 * (-2 d)  in scaled coordinates
     const float dz_scale = (float)(-2.0 * LN2_D);

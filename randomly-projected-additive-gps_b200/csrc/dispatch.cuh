@@ -24,6 +24,8 @@ inline int default_poly_pairs(int CP, int TP) {
     if (TP > 16) return 0;
     return CP >= 28 ? 3 : (CP >= 16 ? 2 : (CP >= 8 ? 1 : 0));
 }
+int launch_fwd_k1_base(int CP, int TP, int base, const MvmArgs& a, dim3 grid, cudaStream_t st);    // Matern-1.5 / inverse MQ, K = 1, TP in {4, 16}
+int launch_grad_k1_base(int CP, int TP, int base, const GradArgs& a, dim3 grid, cudaStream_t st);
 int launch_fwd_kn(int KP, int G, int CP, int TP, int base, const MvmArgs& a, dim3 grid, cudaStream_t st);
 int launch_grad_k1(int CP, int TP, const GradArgs& a, dim3 grid, cudaStream_t st);
 int launch_grad_kn(int KP, int G, int CP, int TP, int base, const GradArgs& a, dim3 grid, cudaStream_t st);

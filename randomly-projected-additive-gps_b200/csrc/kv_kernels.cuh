@@ -69,7 +69,7 @@ struct GradArgs {
 template <int CP, int KP, int G>
 struct RowCoords {
     f32x2 z[CP / 2];                      // packed row coordinates
-    f32x2 c2[(KP == 1) ? CP / 2 : 1];     // K=1: packed -log2c per projection pair
+    f32x2 c2[(KP == 1) ? CP / 2 : 1];     // K=1: packed -log2c per projection pair (RBF) or packed weights c (other base kernels)
     float cg[(KP == 1) ? 1 : G];          // K>1: -log2c per group
     float cw[(KP == 1) ? 1 : G];          // K>1, non-RBF base kernels: c per group (the weight multiplies outside the base function)
 };
@@ -123,6 +123,47 @@ __device__ __forceinline__ void base_value_slope(float u, float nl, float cw, fl
     }
 }
 
+// K = 1 (one coordinate per projection), non-RBF base kernels, on a packed pair of scaled differences d (natural d = ds / sqrt(log2(e)/2)):
+// no square root is needed -- the distance is |d| -- so every base kernel costs ONE MUFU per projection, like the RBF.
+//   Matern-1.5: q = sqrt3 |d_nat| = |ds| sqrt(MATERN_C);  a = q log2(e);  k = c 2^-a (1 + a ln2);  kz = -(dk/du)/ln2 = 3 c 2^-a
+//   inverse MQ: k = c rsqrt(1 + 2 ln2 ds^2);  kz = k rs^2
+constexpr float MATERN_A = 2.942137020149432f;  // sqrt(MATERN_C) * log2(e)
+constexpr float LN2_F = 0.6931471805599453f;
+template <int BASE>
+__device__ __forceinline__ f32x2 base_value_k1(f32x2 d, f32x2 cw) {
+    float dl, dh;
+    unpack2(d, dl, dh);
+    if constexpr (BASE == BASE_MATERN15) {
+        const float al = fabsf(dl) * MATERN_A, ah = fabsf(dh) * MATERN_A;
+        const f32x2 e = pack2(ex2_ftz(-al), ex2_ftz(-ah));
+        const f32x2 u = fma2(pack2(al, ah), pack2(LN2_F, LN2_F), pack2(1.f, 1.f));
+        return mul2(mul2(cw, e), u);
+    } else {
+        const f32x2 t = fma2(d, mul2(d, pack2(TWO_LN2_F, TWO_LN2_F)), pack2(1.f, 1.f));
+        float tl, th;
+        unpack2(t, tl, th);
+        return mul2(cw, pack2(rsqrt_approx_ftz(tl), rsqrt_approx_ftz(th)));
+    }
+}
+template <int BASE>
+__device__ __forceinline__ void base_value_slope_k1(f32x2 d, f32x2 cw, f32x2& k, f32x2& kz) {
+    float dl, dh;
+    unpack2(d, dl, dh);
+    if constexpr (BASE == BASE_MATERN15) {
+        const float al = fabsf(dl) * MATERN_A, ah = fabsf(dh) * MATERN_A;
+        const f32x2 e = mul2(cw, pack2(ex2_ftz(-al), ex2_ftz(-ah)));
+        k = mul2(e, fma2(pack2(al, ah), pack2(LN2_F, LN2_F), pack2(1.f, 1.f)));
+        kz = mul2(e, pack2(3.f, 3.f));
+    } else {
+        const f32x2 t = fma2(d, mul2(d, pack2(TWO_LN2_F, TWO_LN2_F)), pack2(1.f, 1.f));
+        float tl, th;
+        unpack2(t, tl, th);
+        const f32x2 rs = pack2(rsqrt_approx_ftz(tl), rsqrt_approx_ftz(th));
+        k = mul2(cw, rs);
+        kz = mul2(k, mul2(rs, rs));
+    }
+}
+
 // 2^(-u) for a packed pair on the FMA + ALU pipes instead of the XU pipe (takes load off MUFU, the binding unit):
 // Cody-Waite split with the 1.5*2^23 magic constant (round-to-nearest integer n, |f| <= 1/2), degree-5 minimax polynomial
 // for 2^f (max relative error 7.6e-8, i.e. the accuracy of ex2.approx), exponent inserted by an integer shift-add.
@@ -158,7 +199,7 @@ __device__ __forceinline__ f32x2 exp2_neg_poly2(f32x2 u) {
 // NP2 = number of packed projection pairs per (i,i') whose exponential is evaluated by exp2_neg_poly2 (K = 1 only)
 template <int CP, int KP, int G, int NP2 = 0, int BASE = 0>
 __device__ __forceinline__ float pair_kernel_value(const RowCoords<CP, KP, G>& r, const float* __restrict__ zcol) {
-    static_assert(BASE == 0 || KP > 1, "non-RBF base kernels use the group layouts (K = 1 is stored with KP = 2)");
+    static_assert(BASE == 0 || NP2 == 0, "the polynomial exponential belongs to the RBF kernel");
     // zcol: CP floats of one column in shared memory (16 B aligned)
     f32x2 zj[CP / 2];
 #pragma unroll
@@ -167,7 +208,17 @@ __device__ __forceinline__ float pair_kernel_value(const RowCoords<CP, KP, G>& r
         zj[2 * q] = p.x;
         zj[2 * q + 1] = p.y;
     }
-    if constexpr (KP == 1) {
+    if constexpr (KP == 1 && BASE != 0) {
+        f32x2 s0 = 0ull, s1 = 0ull;
+#pragma unroll
+        for (int q = 0; q < CP / 2; ++q) {
+            const f32x2 e = base_value_k1<BASE>(sub2(r.z[q], zj[q]), r.c2[q]);
+            if (q & 1) s1 = add2(s1, e); else s0 = add2(s0, e);
+        }
+        float lo, hi;
+        unpack2(add2(s0, s1), lo, hi);
+        return lo + hi;
+    } else if constexpr (KP == 1) {
         f32x2 s0 = 0ull, s1 = 0ull;
 #pragma unroll
         for (int q = 0; q < CP / 2; ++q) {
@@ -208,7 +259,7 @@ __device__ __forceinline__ float pair_kernel_value(const RowCoords<CP, KP, G>& r
     }
 }
 
-template <int CP, int KP, int G>
+template <int CP, int KP, int G, int BASE = 0>
 __device__ __forceinline__ void load_row_coords(RowCoords<CP, KP, G>& r, const float* __restrict__ zrow, bool valid,
                                                 const float* __restrict__ nlc) {
 #pragma unroll
@@ -216,7 +267,10 @@ __device__ __forceinline__ void load_row_coords(RowCoords<CP, KP, G>& r, const f
         float2 p = valid ? __ldg(reinterpret_cast<const float2*>(zrow) + q) : make_float2(0.f, 0.f);
         r.z[q] = pack2(p.x, p.y);
     }
-    if constexpr (KP == 1) {
+    if constexpr (KP == 1 && BASE != 0) {      // weights c = 2^-(-log2 c); 0 for padding projections (+inf)
+#pragma unroll
+        for (int q = 0; q < CP / 2; ++q) r.c2[q] = pack2(ex2_ftz(-__ldg(nlc + 2 * q)), ex2_ftz(-__ldg(nlc + 2 * q + 1)));
+    } else if constexpr (KP == 1) {
 #pragma unroll
         for (int q = 0; q < CP / 2; ++q) r.c2[q] = pack2(__ldg(nlc + 2 * q), __ldg(nlc + 2 * q + 1));
     } else {
@@ -273,8 +327,8 @@ __global__ void __launch_bounds__(ROWS_PER_CTA, 2) mvm_fwd_kernel(const MvmArgs 
     }
 
     RowCoords<CP, KP, G> r;
-    load_row_coords<CP, KP, G>(r, a.z1 + (long long)chunk * a.z1_chunk_stride + row * CP, valid,
-                               a.nlc + (long long)chunk * GP);
+    load_row_coords<CP, KP, G, BASE>(r, a.z1 + (long long)chunk * a.z1_chunk_stride + row * CP, valid,
+                                     a.nlc + (long long)chunk * GP);
 
     f32x2 acc[TP / 2], comp[TP / 2];
 #pragma unroll
@@ -378,8 +432,8 @@ __global__ void __launch_bounds__(ROWS_PER_CTA, 1) quad_rowgrad_kernel(const Gra
     }
 
     RowCoords<CP, KP, G> r;
-    load_row_coords<CP, KP, G>(r, a.z1 + (long long)chunk * a.z1_chunk_stride + row * CP, valid,
-                               a.nlc + (long long)chunk * GP);
+    load_row_coords<CP, KP, G, BASE>(r, a.z1 + (long long)chunk * a.z1_chunk_stride + row * CP, valid,
+                                     a.nlc + (long long)chunk * GP);
     f32x2 arow[TP / 2], brow[SYM ? TP / 2 : 1];
 #pragma unroll
     for (int q = 0; q < TP / 2; ++q) {
@@ -438,7 +492,16 @@ __global__ void __launch_bounds__(ROWS_PER_CTA, 1) quad_rowgrad_kernel(const Gra
                 zj[2 * q] = p.x;
                 zj[2 * q + 1] = p.y;
             }
-                    if constexpr (KP == 1) {
+            if constexpr (KP == 1 && BASE != 0) {
+#pragma unroll
+                for (int q = 0; q < CP / 2; ++q) {
+                    const f32x2 d = sub2(r.z[q], zj[q]);
+                    f32x2 kv, kz;
+                    base_value_slope_k1<BASE>(d, r.c2[q], kv, kz);
+                    gc2[q] = fma2(kv, SS, gc2[q]);
+                    gz[q] = fma2(mul2(kz, SS), d, gz[q]);
+                }
+            } else if constexpr (KP == 1) {
 #pragma unroll
                 for (int q = 0; q < CP / 2; ++q) {
                     const f32x2 d = sub2(r.z[q], zj[q]);

@@ -38,6 +38,9 @@ constexpr int P_MAX_D = 128, P_MAX_JK = 112;
 #ifndef P_FENCE_PRODUCER
 #define P_FENCE_PRODUCER 0
 #endif
+#ifndef P_DIAG
+#define P_DIAG 0                  // diagnostic builds only: 1 no global loads, 2 no conversion / stores of the operand images, 4 no output stores, 8 no MMAs
+#endif
 
 // barriers
 constexpr int PB_AFULL = 0;       // [3] producers -> issuer (count P_PROD)
@@ -171,8 +174,6 @@ __global__ void __launch_bounds__(P_THREADS, 1) project_tc_kernel(const ProjArgs
 
     if (warp < P_PROD) {
         // =========================================== producers: X tile -> split operand images ==================================
-        // Two 32-column blocks are in flight per warp: the loads of block it + 1 are issued before block it is converted and stored,
-        // so that ~64 KB per SM are outstanding against the ~1 us HBM latency (16 KB per SM left the kernel at 28 % of the roof).
         constexpr int RW = P_ROWS / P_PROD;      // rows per warp
         const long long nblk = ((ntiles - blockIdx.x + gridDim.x - 1) / gridDim.x) * nkb;      // (tile, k-block) items of this CTA
         auto load_block = [&](long long item, float* x) {
@@ -182,32 +183,43 @@ __global__ void __launch_bounds__(P_THREADS, 1) project_tc_kernel(const ProjArgs
 #pragma unroll
             for (int r = 0; r < RW; ++r) {
                 const long long row = row0 + r;
-                x[r] = (row < a.n && col < d) ? __ldg(a.X + row * a.ldx + col) : 0.f;
+                x[r] = (!(P_DIAG & 1) && row < a.n && col < d) ? __ldg(a.X + row * a.ldx + col) : 0.f;
             }
         };
-        float xa[RW], xb[RW];
-        if (nblk > 0) load_block(0, xa);
-        for (long long it = 0; it < nblk; ++it) {
-            if (it + 1 < nblk) load_block(it + 1, xb);
-            const int st = (int)(it % a.nst);
-            if (it >= a.nst) mbar_wait(&bars[PB_AEMPTY + st], (uint32_t)(((it / a.nst) - 1) & 1));
-            unsigned char* ah = sm + OFF_A + (uint32_t)st * 32768u;
+        // P_PF blocks of loads in flight per warp (a ring of register sets, the loop unrolled over it): 16 warps x 8 rows x 128 B x 4
+        // = 64 KB per SM outstanding against ~1 us of loaded HBM latency
+        constexpr int P_PF = 4;
+        float x[P_PF][RW];
 #pragma unroll
-            for (int r = 0; r < RW; ++r) {
-                const uint32_t rt = (uint32_t)(warp * RW + r);
-                const float h = tf32_rn_p(xa[r]), l = tf32_rn_p(xa[r] - h);
-                const uint32_t off = (rt >> 3) * 1024u + sw128_5(rt & 7u, (uint32_t)lane);
-                *reinterpret_cast<float*>(ah + off) = h;
-                *reinterpret_cast<float*>(ah + 16384u + off) = l;
+        for (int u = 0; u < P_PF - 1; ++u)
+            if (u < nblk) load_block(u, x[u]);
+        for (long long it0 = 0; it0 < nblk; it0 += P_PF) {
+#pragma unroll
+            for (int u = 0; u < P_PF; ++u) {
+                const long long it = it0 + u;
+                if (it < nblk) {
+                    if (it + P_PF - 1 < nblk) load_block(it + P_PF - 1, x[(u + P_PF - 1) % P_PF]);
+                    const int st = (int)(it % a.nst);
+                    if (it >= a.nst) mbar_wait(&bars[PB_AEMPTY + st], (uint32_t)(((it / a.nst) - 1) & 1));
+                    unsigned char* ah = sm + OFF_A + (uint32_t)st * 32768u;
+#pragma unroll
+                    for (int r = 0; r < RW; ++r) {
+                        const uint32_t rt = (uint32_t)(warp * RW + r);
+                        const float h = tf32_rn_p(x[u][r]), l = tf32_rn_p(x[u][r] - h);
+                        const uint32_t off = (rt >> 3) * 1024u + sw128_5(rt & 7u, (uint32_t)lane);
+                        if (!(P_DIAG & 2) || x[u][r] == 12345.678f) {
+                            *reinterpret_cast<float*>(ah + off) = h;
+                            *reinterpret_cast<float*>(ah + 16384u + off) = l;
+                        }
+                    }
+                    // no generic -> async proxy fence here: it would wait for the prefetched global loads (MEMBAR.ALL.CTA) and serialise
+                    // the copy.  The stores are released by the mbarrier arrive; the issuing warp acquires AFULL and fences the proxies
+                    // before its MMAs read the stage (P_FENCE_PRODUCER=1 restores the producer-side fence).
+                    if (P_FENCE_PRODUCER) fence5_async_smem();
+                    __syncwarp();
+                    if (lane == 0) mbar5_arrive(&bars[PB_AFULL + st]);
+                }
             }
-            // no generic -> async proxy fence here: it would wait for the prefetched global loads of the next block (MEMBAR.ALL.CTA) and
-            // serialise the copy.  The stores are released by the mbarrier arrive; the issuing warp acquires AFULL and fences the
-            // proxies before its MMAs read the stage (P_FENCE_PRODUCER=1 restores the producer-side fence).
-            if (P_FENCE_PRODUCER) fence5_async_smem();
-            __syncwarp();
-            if (lane == 0) mbar5_arrive(&bars[PB_AFULL + st]);
-#pragma unroll
-            for (int r = 0; r < RW; ++r) xa[r] = xb[r];
         }
     } else if (warp == P_PROD) {
         // =========================================== MMA issue ===================================================================
@@ -228,7 +240,7 @@ __global__ void __launch_bounds__(P_THREADS, 1) project_tc_kernel(const ProjArgs
                     const uint32_t abase = base + OFF_A + (uint32_t)st * 32768u, bbase = base + (uint32_t)kb * (2u * JKp * 128u);
                     const int nks = min(4, ksteps - kb * 4);
 #pragma unroll 1
-                    for (int ks = 0; ks < nks; ++ks) {
+                    for (int ks = 0; ks < ((P_DIAG & 8) ? 0 : nks); ++ks) {
                         const uint64_t dAh = smem_desc5(abase + ks * 32, 16, 1024, LAYOUT5_SW128);
                         const uint64_t dAl = smem_desc5(abase + 16384u + ks * 32, 16, 1024, LAYOUT5_SW128);
                         const uint64_t dB = smem_desc5(bbase + ks * 32, 16, 1024, LAYOUT5_SW128);
@@ -268,7 +280,7 @@ __global__ void __launch_bounds__(P_THREADS, 1) project_tc_kernel(const ProjArgs
                     for (int idx = lane; idx < 32 * CP; idx += 32) {
                         const uint32_t tv = tb[idx], src = tv & 63u;
                         const float v = src != 63u ? stg[(tv >> 6) * 33u + src] * a.scale : 0.f;
-                        if (idx < lim) dst[idx] = v;
+                        if (idx < lim && (!(P_DIAG & 4) || v == 12345.678f)) dst[idx] = v;
                     }
                 }
                 if (a.Zn && cnt > 0) {

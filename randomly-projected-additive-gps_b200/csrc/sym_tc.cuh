@@ -23,6 +23,27 @@ TcdGate tcd_gate(long long n, const Layout& lay);
 int launch_sym_tcd(const float* zp, long long n, const Layout& lay, const float* nlc, const float* bsplit, double* acc, int nblocks,
                    int rb_begin, int nrb, void* ws, size_t ws_bytes, const unsigned** gate_out, cudaStream_t st);
 
+// Column splits of a launch of `items` = row blocks x coordinate chunks CTAs-per-split on `slots` resident CTA slots (148 SMs x CTAs
+// per SM): every CTA of a split does the same work, so the launch runs in waves and the last one should be full.  The smallest split
+// count whose wave efficiency waves / ceil(waves) reaches 99 % (at least four waves), else the best one; at most `max_splits`
+// (= the number of block offsets).  Round 1 took ceil(16 slots / items): 26.4 waves at n = 1M on one GPU (2.3 % tail), 16.5 on eight.
+inline int pick_splits(long long items, long long max_splits, int slots) {
+    int best = 1;
+    double best_eff = 0.0;
+    const long long cap = max_splits < 64 ? max_splits : 64;
+    for (long long s = 1; s <= cap; ++s) {
+        const double waves = (double)(items * s) / slots;
+        const double full = (double)(long long)(waves + 0.999999);
+        // the last split of a row block may be shorter: per = ceil(max_splits / s) offsets, the others carry the imbalance
+        const long long per = (max_splits + s - 1) / s;
+        const double balance = (double)max_splits / (double)(per * s);
+        const double eff = waves / full * balance;
+        if (waves >= 4.0 && eff >= 0.99) return (int)s;
+        if (eff > best_eff + 1e-9) { best_eff = eff; best = (int)s; }
+    }
+    return best;
+}
+
 // FP64 accumulators [n][16] (rounded up to 1 KB) + the pre-split right-hand sides (16 KB per 128-row block) + slack
 inline size_t sym_base_workspace_bytes(long long n) {
     return (((size_t)n * 16 * sizeof(double) + 1023) & ~(size_t)1023) + (size_t)((n + 127) / 128) * 16384 + 1024;

@@ -138,7 +138,7 @@ __global__ void __launch_bounds__(128 * HALVES + 128, 2) mvm_sym_tc5_kernel(cons
         const long long row = (long long)it.I * T5_ROWS + rtid;
         const bool valid = row < a.n;
         RowCoords<CP, KP, G> r;
-        load_row_coords<CP, KP, G>(r, zc + row * CP, valid, a.nlc + (int)blockIdx.z * GP);
+        load_row_coords<CP, KP, G, BASE>(r, zc + row * CP, valid, a.nlc + (int)blockIdx.z * GP);
         f32x2 acc[FC / 2], comp[FC / 2];
 #pragma unroll
         for (int q = 0; q < FC / 2; ++q) { acc[q] = 0ull; comp[q] = 0ull; }
@@ -416,13 +416,27 @@ int launch_sym_tc5(const float* zp, long long n, const Layout& lay, const float*
         a.half = nblocks / 2 + 1;
         a.rb_begin = rb_begin;
         static const int splits_env = [] { const char* e = getenv("RPGP_SYM_SPLITS"); return e ? atoi(e) : 0; }();
-        long long want = (148LL * 2 * 16 + (long long)nrb * lay.nchunks - 1) / ((long long)nrb * lay.nchunks);
+        long long want = pick_splits((long long)nrb * lay.nchunks, a.half, 148 * 2);      // two CTAs per SM
         if (splits_env > 0) want = splits_env;
         want = std::max<long long>(1, std::min<long long>(want, a.half));
         a.nsplits = (int)want;
         dim3 grid((unsigned)nrb, (unsigned)a.nsplits, (unsigned)lay.nchunks);
         int rc = ERR_UNSUPPORTED;
-        if (KP == 1) {
+        if (KP == 1 && lay.base != 0) {
+            // K = 1 with the Matern-1.5 / inverse-multiquadric base kernel: one MUFU per projection (no square root: the distance is |d|)
+#define RPGP_SYM5_K1B(CPv)                                                                                             \
+            if (CP == CPv) {                                                                                           \
+                if constexpr (CPv <= 24)                                                                               \
+                    rc = lay.base == BASE_MATERN15 ? run_sym5<CPv, 1, CPv, 0, 2, BASE_MATERN15>(a, grid, st)           \
+                                                   : run_sym5<CPv, 1, CPv, 0, 2, BASE_IMQ>(a, grid, st);               \
+                else                                                                                                   \
+                    rc = lay.base == BASE_MATERN15 ? run_sym5<CPv, 1, CPv, 0, 1, BASE_MATERN15>(a, grid, st)           \
+                                                   : run_sym5<CPv, 1, CPv, 0, 1, BASE_IMQ>(a, grid, st);               \
+            }
+            RPGP_SYM5_K1B(4) RPGP_SYM5_K1B(8) RPGP_SYM5_K1B(12) RPGP_SYM5_K1B(16) RPGP_SYM5_K1B(20) RPGP_SYM5_K1B(24) RPGP_SYM5_K1B(28) RPGP_SYM5_K1B(32)
+#undef RPGP_SYM5_K1B
+            if (rc == ERR_UNSUPPORTED) set_error("mvm_sym: no K=1 kernel for CP=%d base=%d", CP, lay.base);
+        } else if (KP == 1) {
             // polynomial-exp2 pairs (kv_kernels.cuh::exp2_neg_poly2); RPGP_SYM_POLY_PAIRS overrides (tools sweep)
             static const int np_env = [] { const char* e = getenv("RPGP_SYM_POLY_PAIRS"); return e ? atoi(e) : -1; }();
             const int np = np_env >= 0 ? np_env : (CP >= 20 ? 2 : (CP >= 16 ? 1 : 0));

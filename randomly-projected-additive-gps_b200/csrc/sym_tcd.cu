@@ -793,7 +793,7 @@ int launch_sym_tcd(const float* zp, long long n, const Layout& lay, const float*
     }
 #endif
     static const int splits_env = [] { const char* e = getenv("RPGP_SYM_SPLITS"); return e ? atoi(e) : 0; }();
-    long long want = (148LL * 16 + (long long)nrb * p.nchunks - 1) / ((long long)nrb * p.nchunks);
+    long long want = pick_splits((long long)nrb * p.nchunks, a.half, 148);      // one CTA per SM
     if (splits_env > 0) want = splits_env;
     want = std::max<long long>(1, std::min<long long>(want, a.half));
     a.nsplits = (int)want;

@@ -251,12 +251,11 @@ def test_distance_on_tensor_core_plan_and_base_layouts():
     assert (plan["groups_per_chunk"], plan["ksteps_per_group"], plan["lines"], plan["nchunks"]) == (3, 2, 2, 2)
     for J, K in [(20, 1), (10, 3), (1, 30)]:          # K = 1, K below the cross-over, K too wide: direct differences only
         assert _lib.mvm_sym_distance_plan(_lib.plan_layout(J, K)) is None
-    # non-RBF base kernels: group layouts even for K = 1 (few wide chunks: every chunk is a full pass of the symmetric kernel), the
-    # symmetric tensor-core kernel but not its distance-on-tensor-core variant, fewer right-hand-side widths
+    # non-RBF base kernels: the same layouts as the RBF (K = 1: one coordinate per projection), the symmetric tensor-core kernel but
+    # not its distance-on-tensor-core variant, fewer right-hand-side widths
     rbf, mat = _lib.plan_layout(20, 1), _lib.plan_layout(20, 1, _lib.BASE_MATERN15)
     assert (rbf.base, rbf.KP, rbf.G, rbf.CP) == (0, 1, 20, 20)
-    assert mat.base == 1 and mat.KP == 2 and mat.K == 1 and mat.G * mat.nchunks >= 20 and mat.G * mat.KP <= mat.CP
-    assert (mat.KP, mat.G, mat.CP, mat.nchunks) == (2, 16, 32, 2)
+    assert mat.base == 1 and (mat.KP, mat.G, mat.CP, mat.nchunks, mat.K) == (1, 20, 20, 1, 1)
     assert _lib.mvm_sym_supported(rbf, 11) and _lib.mvm_sym_supported(mat, 11) and not _lib.mvm_sym_supported(mat, 17)
     assert _lib.mvm_sym_distance_plan(_lib.plan_layout(20, 5, _lib.BASE_INVERSE_MQ)) is None
     assert _lib.padded_rhs(mat, 11, False) == 16 and _lib.padded_rhs(rbf, 11, False) == 12

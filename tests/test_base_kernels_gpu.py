@@ -53,7 +53,8 @@ def test_symmetric_tensor_core_kernel_with_other_base_kernels(base, n, J, K, t):
     """square products of n >= 1024 rows go to the symmetric tcgen05 kernel for every base kernel (round 2): against the oracle (1e-5)
     and against the SIMT forward kernel on the same packed operands"""
     from rpgp import _lib
-    Z, _, c, V = data(n, 3, J, K, t, seed=n + J + K + base)
+    Z, _, c, _ = data(n, 3, J, K, t, seed=n + J + K + base)
+    V = np.random.RandomState(n + t).randn(n, t).astype(np.float32)
     d = lambda a: torch.from_numpy(a).to(DEV)      # noqa: E731
     lay = _lib.plan_layout(J, K, base)
     assert _lib.mvm_sym_supported(lay, t)

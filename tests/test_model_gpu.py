@@ -403,6 +403,53 @@ def test_train_exact_gp_end_to_end_cfg1_shape():
     assert abs(metrics["test_nll"] - ref_nll) / abs(ref_nll) < 0.01, (metrics["test_nll"], ref_nll)
 
 
+def test_cfg1_at_its_named_size_train_and_predict():
+    """BASELINE configs[0] at the size it names (synthetic_test_script.py:96-108,122-123): n = 2000 points of the 10-dimensional
+    `additive` target (noise 0.01), 4000 hold-out points of the same law, both standardised by the HOLD-OUT statistics, spec
+    additive_rp_J20_K1, cg_tolerance 1e-3, eval_cg_tolerance 5e-4, max_cg_iterations 10 000, Adam lr 0.1.  The trained model's
+    held-out RMSE (the quantity the script reports) must agree with the dense FP64 oracle evaluated at the SAME trained
+    hyper-parameters to 1 %."""
+    import synthetic_test_script as sts
+    g = torch.Generator().manual_seed(0)
+    n, nho, d = 2000, 4000, 10
+    ho_x = torch.rand(nho, d, generator=g) * 4 - 2
+    ho_y = sts.additive(ho_x) + torch.randn(nho, generator=g) * 0.01
+    X = torch.rand(n, d, generator=g) * 4 - 2
+    y = sts.additive(X) + torch.randn(n, generator=g) * 0.01
+    mx, sx, my, sy = ho_x.mean(0), ho_x.std(0), ho_y.mean(), ho_y.std()
+    X, Xt, y, yt = ((X - mx) / sx).to(DEV), ((ho_x - mx) / sx).to(DEV), ((y - my) / sy).to(DEV), ((ho_y - my) / sy).to(DEV)
+    spec = tr.load_model_spec("additive_rp_J20_K1")
+    spec["train_kwargs"].update(max_iter=30, check_conv=False, lr=0.1)
+    torch.manual_seed(0)
+    np.random.seed(0)
+    import time
+    t0 = time.perf_counter()
+    with settings.cg_tolerance(1e-3), settings.eval_cg_tolerance(5e-4), settings.max_cg_iterations(10_000), warnings.catch_warnings():
+        warnings.simplefilter("ignore")
+        metrics, pred_mean, model = tr.train_exact_gp(X, y, Xt, yt, spec["kind"], spec["model_kwargs"], spec["train_kwargs"],
+                                                      devices=("cuda:0",), skip_random_restart=True)
+    torch.cuda.synchronize()
+    print("cfg1 (n=2000, d=10, J=20): 30 epochs + evaluation in %.1f s" % (time.perf_counter() - t0))
+    assert metrics["trained_epochs"] == 30
+    rmse = float(((pred_mean - yt.cpu()) ** 2).mean().sqrt())
+    assert rmse < 0.35, rmse                                          # (30 epochs from a random initialisation)
+    m = copy.deepcopy(model).to("cpu", torch.float64)
+    opx = m.covar_module(X.cpu().double()).evaluate_kernel()
+    opt = m.covar_module(Xt.cpu().double(), X.cpu().double()).evaluate_kernel()
+    noise = m.likelihood.noise.item()
+    args = (opx.c.detach().numpy(), opx.J, opx.K, noise, y.cpu().numpy().astype(np.float64), m.mean_module.constant.item())
+    ref_mean, ref_cov = orc.predict_dense(opx.Z1.detach().numpy(), opt.Z1.detach().numpy(), *args, full_cov=True)
+    ref_rmse = float(np.sqrt(((ref_mean - yt.cpu().numpy()) ** 2).mean()))
+    assert abs(rmse - ref_rmse) / ref_rmse < 0.01, (rmse, ref_rmse)
+    # The script reports only the hold-out MSE for this configuration (synthetic_test_script.py:124-127).  The joint test log-probability
+    # that train_exact_gp also records is NOT compared here: with noise 0.01 the 4000 x 4000 predictive covariance is numerically
+    # singular and a CG solve at eval_cg_tolerance 5e-4 (the script's setting, as in GPyTorch) does not determine it -- the 1 % NLL
+    # check lives in test_train_exact_gp_end_to_end_cfg1_shape (noise 0.05, eval tolerance 1e-4).
+    assert np.isfinite(metrics["test_nll"])
+    pred_var_ref = np.diag(ref_cov) + noise
+    assert np.all(pred_var_ref > 0)
+
+
 def test_experiment_runner_end_to_end(tmp_path):
     """the reference's UCI protocol through gp_experiment_runner.main -- spec file, fold split, train-set
     normalisation, solver flags (with --fast_pred: LOVE variances), train_exact_gp on the fused kernels, CSV on disk."""
