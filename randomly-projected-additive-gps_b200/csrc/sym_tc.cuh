@@ -25,7 +25,7 @@ int launch_sym_tcd(const float* zp, long long n, const Layout& lay, const float*
 
 // Column splits of a launch of `items` = row blocks x coordinate chunks CTAs-per-split on `slots` resident CTA slots (148 SMs x CTAs
 // per SM): every CTA of a split does the same work, so the launch runs in waves and the last one should be full.  The smallest split
-// count whose wave efficiency waves / ceil(waves) reaches 99 % (at least four waves), else the best one; at most `max_splits`
+// count whose wave efficiency waves / ceil(waves) reaches 98.5 % (at least eight waves), else the best one; at most `max_splits`
 // (= the number of block offsets).  Round 1 took ceil(16 slots / items): 26.4 waves at n = 1M on one GPU (2.3 % tail), 16.5 on eight.
 inline int pick_splits(long long items, long long max_splits, int slots) {
     int best = 1;
@@ -38,7 +38,7 @@ inline int pick_splits(long long items, long long max_splits, int slots) {
         const long long per = (max_splits + s - 1) / s;
         const double balance = (double)max_splits / (double)(per * s);
         const double eff = waves / full * balance;
-        if (waves >= 4.0 && eff >= 0.99) return (int)s;
+        if (waves >= 8.0 && eff >= 0.985) return (int)s;
         if (eff > best_eff + 1e-9) { best_eff = eff; best = (int)s; }
     }
     return best;
