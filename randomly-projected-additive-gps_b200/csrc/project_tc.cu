@@ -174,39 +174,51 @@ __global__ void __launch_bounds__(P_THREADS, 1) project_tc_kernel(const ProjArgs
 
     if (warp < P_PROD) {
         // =========================================== producers: X tile -> split operand images ==================================
+        // The kernel is issue-bound before it is HBM-bound (ncu, profiles/ncu_r02_project_cfg4_summary.md: ALU pipe 53 %, issue 68 %), so the
+        // producer loop is written for instruction count: 32-bit counters advanced incrementally (no 64-bit division per block), one
+        // 64-bit pointer per block, shared-memory offsets that are compile-time functions of the row, guards only where they can fail.
         constexpr int RW = P_ROWS / P_PROD;      // rows per warp
-        const long long nblk = ((ntiles - blockIdx.x + gridDim.x - 1) / gridDim.x) * nkb;      // (tile, k-block) items of this CTA
-        auto load_block = [&](long long item, float* x) {
-            const long long tile = blockIdx.x + (item / nkb) * gridDim.x;
-            const int col = (int)(item % nkb) * 32 + lane;
-            const long long row0 = tile * P_ROWS + warp * RW;
+        constexpr int P_PF = 4;                  // blocks of loads in flight per warp (a ring of register sets, the loop unrolled over it)
+        const int my_tiles = (int)((ntiles - blockIdx.x + gridDim.x - 1) / gridDim.x);
+        const int nblk = my_tiles * nkb;         // (tile, k-block) items of this CTA
+        // load cursor (runs P_PF - 1 items ahead of the store cursor)
+        int l_kb = 0;
+        long long l_tile = blockIdx.x;
+        auto load_next = [&](float* x) {
+            const int col = l_kb * 32 + lane;
+            const long long row0 = l_tile * P_ROWS + warp * RW;
+            const float* p = a.X + row0 * a.ldx + col;
+            if (P_DIAG & 1) {
 #pragma unroll
-            for (int r = 0; r < RW; ++r) {
-                const long long row = row0 + r;
-                x[r] = (!(P_DIAG & 1) && row < a.n && col < d) ? __ldg(a.X + row * a.ldx + col) : 0.f;
+                for (int r = 0; r < RW; ++r) x[r] = 0.f;
+            } else if (col < d && row0 + RW <= a.n) {
+#pragma unroll
+                for (int r = 0; r < RW; ++r) x[r] = __ldg(p + r * a.ldx);
+            } else {
+#pragma unroll
+                for (int r = 0; r < RW; ++r) x[r] = (col < d && row0 + r < a.n) ? __ldg(p + r * a.ldx) : 0.f;
             }
+            if (++l_kb == nkb) { l_kb = 0; l_tile += gridDim.x; }
         };
-        // P_PF blocks of loads in flight per warp (a ring of register sets, the loop unrolled over it): 16 warps x 8 rows x 128 B x 4
-        // = 64 KB per SM outstanding against ~1 us of loaded HBM latency
-        constexpr int P_PF = 4;
+        const uint32_t st_base = (uint32_t)warp * 1024u + (uint32_t)(lane & 3) * 4u;      // rows 8 warp .. 8 warp + 7 = one swizzle atom
+        const uint32_t unit = (uint32_t)lane >> 2;
         float x[P_PF][RW];
 #pragma unroll
         for (int u = 0; u < P_PF - 1; ++u)
-            if (u < nblk) load_block(u, x[u]);
-        for (long long it0 = 0; it0 < nblk; it0 += P_PF) {
+            if (u < nblk) load_next(x[u]);
+        int st = 0, use = 0;                     // stage of the store cursor and how often it has been used
+        for (int it0 = 0; it0 < nblk; it0 += P_PF) {
 #pragma unroll
             for (int u = 0; u < P_PF; ++u) {
-                const long long it = it0 + u;
+                const int it = it0 + u;
                 if (it < nblk) {
-                    if (it + P_PF - 1 < nblk) load_block(it + P_PF - 1, x[(u + P_PF - 1) % P_PF]);
-                    const int st = (int)(it % a.nst);
-                    if (it >= a.nst) mbar_wait(&bars[PB_AEMPTY + st], (uint32_t)(((it / a.nst) - 1) & 1));
-                    unsigned char* ah = sm + OFF_A + (uint32_t)st * 32768u;
+                    if (it + P_PF - 1 < nblk) load_next(x[(u + P_PF - 1) % P_PF]);
+                    if (use >= 1) mbar_wait(&bars[PB_AEMPTY + st], (uint32_t)((use - 1) & 1));
+                    unsigned char* ah = sm + OFF_A + (uint32_t)st * 32768u + st_base;
 #pragma unroll
                     for (int r = 0; r < RW; ++r) {
-                        const uint32_t rt = (uint32_t)(warp * RW + r);
                         const float h = tf32_rn_p(x[u][r]), l = tf32_rn_p(x[u][r] - h);
-                        const uint32_t off = (rt >> 3) * 1024u + sw128_5(rt & 7u, (uint32_t)lane);
+                        const uint32_t off = (uint32_t)r * 128u + ((unit ^ (uint32_t)r) << 4);
                         if (!(P_DIAG & 2) || x[u][r] == 12345.678f) {
                             *reinterpret_cast<float*>(ah + off) = h;
                             *reinterpret_cast<float*>(ah + 16384u + off) = l;
@@ -218,6 +230,7 @@ __global__ void __launch_bounds__(P_THREADS, 1) project_tc_kernel(const ProjArgs
                     if (P_FENCE_PRODUCER) fence5_async_smem();
                     __syncwarp();
                     if (lane == 0) mbar5_arrive(&bars[PB_AFULL + st]);
+                    if (++st == a.nst) { st = 0; ++use; }
                 }
             }
         }
@@ -225,15 +238,14 @@ __global__ void __launch_bounds__(P_THREADS, 1) project_tc_kernel(const ProjArgs
         // =========================================== MMA issue ===================================================================
         const uint32_t idesc1 = idesc5_tf32(128, 2 * JKp, 0, 0);
         const int ksteps = (d + 7) / 8;
-        long long it = 0, t = 0;
+        int t = 0, st = 0, use = 0;
         for (long long tile = blockIdx.x; tile < ntiles; tile += gridDim.x, ++t) {
-            const int ab = (int)(t & 1);
+            const int ab = t & 1;
             if (t >= 2) mbar5_wait_sleep<32>(&bars[PB_DEMPTY + ab], (uint32_t)(((t >> 1) - 1) & 1));
             tc5_fence_after();
             const uint32_t dacc = tmem + (uint32_t)(ab * 2 * JKp);
-            for (int kb = 0; kb < nkb; ++kb, ++it) {
-                const int st = (int)(it % a.nst);
-                mbar5_wait_sleep<32>(&bars[PB_AFULL + st], (uint32_t)((it / a.nst) & 1));
+            for (int kb = 0; kb < nkb; ++kb) {
+                mbar5_wait_sleep<32>(&bars[PB_AFULL + st], (uint32_t)(use & 1));
                 if (!P_FENCE_PRODUCER) fence5_async_smem();
                 tc5_fence_after();
                 if (elect_one()) {
@@ -251,6 +263,7 @@ __global__ void __launch_bounds__(P_THREADS, 1) project_tc_kernel(const ProjArgs
                     if (kb == nkb - 1) umma5_commit(&bars[PB_DFULL + ab]);
                 }
                 __syncwarp();
+                if (++st == a.nst) { st = 0; ++use; }
             }
         }
     } else {

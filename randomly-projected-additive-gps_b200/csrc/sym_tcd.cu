@@ -97,11 +97,11 @@ constexpr int BD_BCFULL = 18;    // [1]  bulk copy of the column-side B operand
 constexpr int BD_AFULL = 19;     // [1]  the A image is in tensor memory (count 4: the warps of rows 0..127)
 constexpr int BD_D0FULL = 20;    // [2 teams][D_NBUF]  tcgen05.commit of the team's distance issuer for a batch of two groups
 constexpr int BD_D0FREE = 20 + 2 * D_NBUF;   // [2 teams][D_NBUF]  the team's warps have read the batch (count 8)
-constexpr int BD_STAG = 31;      // [1]  team 0 is half-way through the exponentials of its tile (count 8): team 1 starts its tile then
-static_assert(BD_D0FREE + 2 * D_NBUF <= BD_STAG, "barrier block is 256 bytes");
-#ifndef TCD_STAGGER
-#define TCD_STAGGER 0            // (experiment, no gain) keep the two teams half a tile out of phase: one team's waits, TMEM loads, S stores and fences then run
-#endif                           // under the other's exponentials instead of both idling the XU pipe together (profiles/tcd_timeline_r02.txt)
+constexpr int BD_XTURN = 30;     // [2]  [T]: the other team has finished the exponentials of a tile (count 8): team T's turn
+static_assert(BD_D0FREE + 2 * D_NBUF <= BD_XTURN, "barrier block is 256 bytes");
+#ifndef TCD_PINGPONG
+#define TCD_PINGPONG 0           // 1 (experiment, 40-60 % SLOWER for 7-8 groups per tile): the exponential phases of the two teams alternate
+#endif
 #ifndef TCD_FENCE_ISSUER
 #define TCD_FENCE_ISSUER 0       // 0: every arithmetic warp fences its S stores (generic -> async proxy) before SFULL; 1 (experiment,
 #endif                           // same speed, parity tests pass): one fence by the S-side issuer after it has acquired SFULL
@@ -214,7 +214,8 @@ __global__ void __maxnreg__(80) mvm_sym_tcd_kernel(const SymDArgs a) {
         }
         mbar_init(&bars[BD_BCFULL], 1);
         mbar_init(&bars[BD_AFULL], 4);
-        mbar_init(&bars[BD_STAG], D_AW / 2);
+        mbar_init(&bars[BD_XTURN + 0], D_AW / 2);
+        mbar_init(&bars[BD_XTURN + 1], D_AW / 2);
 #pragma unroll
         for (int s = 0; s < 2 * D_NBUF; ++s) {
             mbar_init(&bars[BD_D0FULL + s], 1);
@@ -313,6 +314,7 @@ __global__ void __maxnreg__(80) mvm_sym_tcd_kernel(const SymDArgs a) {
         };
 #pragma unroll
         for (int q = 0; q < 32; ++q) un[q] = 0u;
+        const uint32_t tbase = tmem + D_TM_D0 + (uint32_t)(half * 16) + lanes;      // this thread's 16 columns of a D0 group
         int j = 0, folded = 0;       // j counts the live tiles of BOTH teams
         uint32_t item = 0, ibuf = 0, iuse = 0;   // this team's (tile, batch) counter, item % D_NBUF, item / D_NBUF
         for (int t = it.next_live(0); t < it.ntiles; t = it.next_live(t + 1), ++j) {
@@ -321,7 +323,6 @@ __global__ void __maxnreg__(80) mvm_sym_tcd_kernel(const SymDArgs a) {
             const long long c0 = it.col0(t) + half * 16;
             const bool diag = it.diag(t);
             if (tid == 0 || tid == 256) TCD_STAMP(j, 3);
-            if (TCD_STAGGER && team == 1) mbar_wait(&bars[BD_STAG], (uint32_t)((j >> 1) & 1));      // (team 0's tile j - 1)
             float s[16];
 #pragma unroll
             for (int c = 0; c < 16; ++c) s[c] = 0.f;
@@ -340,28 +341,108 @@ __global__ void __maxnreg__(80) mvm_sym_tcd_kernel(const SymDArgs a) {
 #pragma unroll
                 for (int c = 0; c < 16; ++c) s[c] += ex2_ftz(-u[c]);
             };
-            // (tried in round 2 and not kept: issuing the tcgen05.ld of the next group under the exponentials of the current one --
-            // no gain, profiles/tcd_variants_r02.txt: with 16 free-running warps the loads already overlap the other warps' MUFU work)
+#if TCD_PINGPONG
+            // The exponential phases of the two teams alternate (FlashAttention-3 style ping-pong): a team starts the exponentials of
+            // its tile when the other team has finished those of ITS tile, so that one team's waits, S stores, fences and barrier round
+            // trips run under the other's MUFU work instead of both idling the XU pipe together (the teams otherwise fall into lockstep:
+            // profiles/tcd_variants_r02.txt).  Inside its phase the team runs alone, so the tcgen05.ld of the next group is issued under
+            // the exponentials of the current one (tcgen05.wait::ld waits for ALL outstanding loads: every load is issued right after
+            // the wait for the previous one).
+            {
+                const uint32_t turn = (uint32_t)(j >> 1);       // index of this team's tile
+                if (team == 1) mbar_wait(&bars[BD_XTURN + 1], turn & 1u);
+                else if (turn >= 1) mbar_wait(&bars[BD_XTURN + 0], (turn - 1) & 1u);
+            }
+            uint32_t buf = (uint32_t)(D_NBUF * team) + ibuf;
+            mbar_wait(&bars[BD_D0FULL + buf], iuse & 1u);
+            if (tid == 0 || tid == 256) TCD_STAMP(j, 4);
+            tc5_fence_after();
+            ld_group(64u * buf, 0);
             for (int k = 0; k < NB; ++k, ++item) {
                 const int g0 = 2 * k, gcnt = min(2, G - g0);
+                ld_wait();                                            // group g0 is in slot 0
+                if (gcnt > 1) ld_group(64u * buf, 1);                 // second group of the batch -> slot 1, under the exponentials of slot 0
+                if (gcnt == 1) {                                      // (single-group last batch: fully read)
+                    tc5_fence_before();
+                    __syncwarp();
+                    if (lane == 0) mbar5_arrive(&bars[BD_D0FREE + buf]);
+                }
+                exp_group(0, g0);
+                if (gcnt > 1) {
+                    ld_wait();                                        // group g0 + 1 is in slot 1: the batch has been read
+                    tc5_fence_before();
+                    __syncwarp();
+                    if (lane == 0) mbar5_arrive(&bars[BD_D0FREE + buf]);
+                }
+                if (++ibuf == D_NBUF) { ibuf = 0; ++iuse; }
+                if (k + 1 < NB) {                                     // first group of the next batch -> slot 0, under the exponentials of slot 1
+                    buf = (uint32_t)(D_NBUF * team) + ibuf;
+                    mbar_wait(&bars[BD_D0FULL + buf], iuse & 1u);
+                    tc5_fence_after();
+                    ld_group(64u * buf, 0);
+                }
+                if (gcnt > 1) exp_group(1, g0 + 1);
+            }
+            __syncwarp();
+            if (lane == 0) mbar5_arrive(&bars[BD_XTURN + (1 - team)]);      // the other team's turn
+#else
+            // one batch = two groups: both tcgen05.ld and their wait are ONE asm statement with plain outputs, so that the exponents go
+            // from the load's destination registers straight into MUFU.EX2 (the earlier form kept them in an array tied to a separate
+            // wait statement and ptxas copied all of them: 17 % of the arithmetic warps' instructions, which run at 83 % of the issue
+            // budget of the XU-bound tile -- profiles/ncu_r02_tcd_cfg5b_summary.md)
+            for (int k = 0; k < NB; ++k, ++item) {
+                const int g0 = 2 * k;
+                const bool two = g0 + 1 < G;
                 const uint32_t buf = (uint32_t)(D_NBUF * team) + ibuf;
                 mbar_wait(&bars[BD_D0FULL + buf], iuse & 1u);
                 if (k == 0 && (tid == 0 || tid == 256)) TCD_STAMP(j, 4);
                 if (++ibuf == D_NBUF) { ibuf = 0; ++iuse; }
                 tc5_fence_after();
-                ld_group(64u * buf, 0);
-                if (gcnt > 1) ld_group(64u * buf, 1);
-                ld_wait();
+                const uint32_t ta = tbase + 64u * buf;
+                uint32_t w[32];
+                if (two) {
+                    asm volatile(
+                        "tcgen05.ld.sync.aligned.32x32b.x16.b32 {%0,%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15}, [%32];\n\t"
+                        "tcgen05.ld.sync.aligned.32x32b.x16.b32 {%16,%17,%18,%19,%20,%21,%22,%23,%24,%25,%26,%27,%28,%29,%30,%31}, [%33];\n\t"
+                        "tcgen05.wait::ld.sync.aligned;"
+                        : "=r"(w[0]), "=r"(w[1]), "=r"(w[2]), "=r"(w[3]), "=r"(w[4]), "=r"(w[5]), "=r"(w[6]), "=r"(w[7]), "=r"(w[8]), "=r"(w[9]),
+                          "=r"(w[10]), "=r"(w[11]), "=r"(w[12]), "=r"(w[13]), "=r"(w[14]), "=r"(w[15]), "=r"(w[16]), "=r"(w[17]), "=r"(w[18]),
+                          "=r"(w[19]), "=r"(w[20]), "=r"(w[21]), "=r"(w[22]), "=r"(w[23]), "=r"(w[24]), "=r"(w[25]), "=r"(w[26]), "=r"(w[27]),
+                          "=r"(w[28]), "=r"(w[29]), "=r"(w[30]), "=r"(w[31])
+                        : "r"(ta), "r"(ta + 32u)
+                        : "memory");
+                } else {
+                    asm volatile(
+                        "tcgen05.ld.sync.aligned.32x32b.x16.b32 {%0,%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15}, [%16];\n\t"
+                        "tcgen05.wait::ld.sync.aligned;"
+                        : "=r"(w[0]), "=r"(w[1]), "=r"(w[2]), "=r"(w[3]), "=r"(w[4]), "=r"(w[5]), "=r"(w[6]), "=r"(w[7]), "=r"(w[8]), "=r"(w[9]),
+                          "=r"(w[10]), "=r"(w[11]), "=r"(w[12]), "=r"(w[13]), "=r"(w[14]), "=r"(w[15])
+                        : "r"(ta)
+                        : "memory");
+                }
                 tc5_fence_before();
                 __syncwarp();
                 if (lane == 0) mbar5_arrive(&bars[BD_D0FREE + buf]);
-                exp_group(0, g0);
-                if (gcnt > 1) exp_group(1, g0 + 1);
-                if (TCD_STAGGER && team == 0 && k == (NB - 1) / 2) {
-                    __syncwarp();
-                    if (lane == 0) mbar5_arrive(&bars[BD_STAG]);
+                if (diag) {     // a pair with itself: the exact exponent (no cancellation error on the dominant entries of K)
+#pragma unroll
+                    for (int gb = 0; gb < 2; ++gb) {
+                        if (gb == 0 || two) {
+                            const int jg = chunk * G + g0 + gb;
+                            const float nl = jg < a.J ? __ldg(a.nlc + jg) : D_PAD;
+#pragma unroll
+                            for (int c = 0; c < 16; ++c)
+                                if (c0 + c == row) w[16 * gb + c] = __float_as_uint(nl);
+                        }
+                    }
+                }
+#pragma unroll
+                for (int c = 0; c < 16; ++c) s[c] += ex2_ftz(-__uint_as_float(w[c]));
+                if (two) {
+#pragma unroll
+                    for (int c = 0; c < 16; ++c) s[c] += ex2_ftz(-__uint_as_float(w[16 + c]));
                 }
             }
+#endif
             if (tid == 0 || tid == 256) TCD_STAMP(j, 1);
             if (j >= 2) {   // only now is the S buffer needed: tile j-2 has left the tensor core (its exponentials ran under the S-side
                             // MMAs of the team's previous tile), and -- the S-side issuer commits in tile order -- every row-side epoch

@@ -68,6 +68,16 @@ class max_cg_iterations(_Value):
     _default = 1000
 
 
+class cg_convergence_lag(_Value):
+    """How many iterations late the host may learn that CG has converged (not a GPyTorch setting).  GPyTorch reads the residual norm
+    on the host after EVERY iteration (a device synchronisation per iteration).  -1 (default): 0 for products of >= 2^22 kernel-matrix
+    rows x right-hand sides (the iteration is device-bound: an extra iteration costs more than the synchronisation), 2 below that
+    (launch-bound sizes such as BASELINE configs[0]: the residual norm is copied to pinned memory asynchronously and read two
+    iterations later, so the host keeps launching; the solve runs up to two iterations past GPyTorch's stopping point -- never
+    fewer -- and reports the residual it actually reached).  0 restores GPyTorch's iteration counts exactly."""
+    _default = -1
+
+
 class max_cholesky_size(_Value):
     _default = 800
 

@@ -78,6 +78,15 @@ def linear_cg(matmul_closure, rhs, n_tridiag=0, tolerance=1.0, eps=None, stop_up
     update_tridiag = True
     last_tridiag_iter = 0
     tolerance_reached = False
+    # convergence is tested on the host; on CUDA the mean residual norm travels through pinned memory and may be read `lag`
+    # iterations late (settings.cg_convergence_lag) so that small, launch-bound solves do not synchronise every iteration
+    lag = 0
+    if rhs.is_cuda:
+        from ..gp import settings as _s
+        lag = _s.cg_convergence_lag.value()
+        if lag < 0:
+            lag = 0 if n * t >= (1 << 22) else 2
+    pending = []          # (iteration, pinned scalar, event) of residual norms not yet read
     k = -1
     for k in range(n_iter):
         mvms = matmul_closure(curr_conjugate_vec)
@@ -120,10 +129,27 @@ def linear_cg(matmul_closure, rhs, n_tridiag=0, tolerance=1.0, eps=None, stop_up
             prev_alpha_recip = alpha_recip.clone()
             prev_beta = beta_t.clone()
 
-        if (k >= min(10, max_iter - 1) and float(residual_norm.mean()) < tolerance
-                and not (n_tridiag and k < min(n_tridiag_iter, max_iter - 1))):
-            tolerance_reached = True
-            break
+        if k >= min(10, max_iter - 1) and not (n_tridiag and k < min(n_tridiag_iter, max_iter - 1)):
+            if lag == 0:
+                if float(residual_norm.mean()) < tolerance:
+                    tolerance_reached = True
+                    break
+            else:
+                host = torch.empty((), dtype=residual_norm.dtype, pin_memory=True)
+                host.copy_(residual_norm.mean(), non_blocking=True)
+                ev = torch.cuda.Event()
+                ev.record()
+                pending.append((k, host, ev))
+                if len(pending) > lag:
+                    _, h, e = pending.pop(0)
+                    e.synchronize()
+                    if float(h) < tolerance:
+                        tolerance_reached = True
+                        break
+    if lag and not tolerance_reached and pending:      # max_iter reached with unread norms: the last one decides
+        _, h, e = pending[-1]
+        e.synchronize()
+        tolerance_reached = float(h) < tolerance
 
     STATS["solves"] += 1
     STATS["iterations"] += k + 1

@@ -4,7 +4,7 @@ mkdir -p gpurun_out
 timeout 900 python -m pytest tests/test_sym_tc_gpu.py -x -q > gpurun_out/pytest_f.txt 2>&1
 echo "pytest rc=$?" >> gpurun_out/pytest_f.txt
 {
-for v in "" d47; do
+for v in "" pp0; do
   if [ -n "$v" ]; then export RPGP_LIB=$PWD/build/librpgp_$v.so; else unset RPGP_LIB; fi
   for shape in "100000 20 5" "100000 1 20" "100000 8 6"; do
     echo -n "variant=${v:-default} "; timeout 120 python tools/tcd_check.py time $shape 2>&1 | tail -1
