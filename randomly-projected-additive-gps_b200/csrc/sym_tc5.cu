@@ -43,6 +43,9 @@ constexpr int T5_ZST = 3;        // coordinate-tile stages
 #define T5_DIAG 0                // diagnostic builds only (tools/sym5_variants.sh): 1 no column-side atomics, 2 no column-side MMAs, 4 no row-side MMAs
 #endif
 constexpr int T5_QU = T5_QUNROLL;   // unroll factor of the 4-column groups inside a tile
+#ifndef T5_FENCE_ISSUER
+#define T5_FENCE_ISSUER 0        // 1 (experiment): the generic -> async proxy fence for the S tile by the two issuing warps after they have
+#endif                           // acquired SFULL, instead of by every arithmetic warp (MEMBAR.ALL.CTA once per tile and warp)
 #ifndef T5_REGS_ARITH
 #define T5_REGS_ARITH 184
 #endif
@@ -196,7 +199,7 @@ __global__ void __launch_bounds__(128 * HALVES + 128, 2) mvm_sym_tc5_kernel(cons
                 }
             };
             if (cols == T5_BN) tile_body(std::true_type{}); else tile_body(std::false_type{});
-            fence5_async_smem();
+            if (!T5_FENCE_ISSUER) fence5_async_smem();
             __syncwarp();
             if (lane == 0) mbar5_arrive(&bars[B5_SFULL + b]);
         }
@@ -273,6 +276,7 @@ __global__ void __launch_bounds__(128 * HALVES + 128, 2) mvm_sym_tc5_kernel(cons
                 mbar5_wait_sleep(&bars[B5_BFULL + b], (uint32_t)((j >> 1) & 1));
                 if (j % T5_F == 0 && e >= 2) mbar5_wait_sleep(&bars[B5_D1EMPTY + (e & 1)], (uint32_t)(((e >> 1) - 1) & 1));
                 mbar5_wait_sleep(&bars[B5_SFULL + b], (uint32_t)((j >> 1) & 1));
+                if (T5_FENCE_ISSUER) fence5_async_smem();
                 tc5_fence_after();
                 if (elect_one()) {
                     if (!(T5_DIAG & 4)) {
@@ -295,6 +299,7 @@ __global__ void __launch_bounds__(128 * HALVES + 128, 2) mvm_sym_tc5_kernel(cons
                 if (j == 0) mbar5_wait_sleep(&bars[B5_BCFULL], 0u);
                 if (j >= 2) mbar5_wait_sleep(&bars[B5_EREAD + b], (uint32_t)(((j >> 1) - 1) & 1));        // D2[b] has been read
                 mbar5_wait_sleep(&bars[B5_SFULL + b], (uint32_t)((j >> 1) & 1));
+                if (T5_FENCE_ISSUER) fence5_async_smem();
                 tc5_fence_after();
                 if (elect_one()) {
                     if (!diag && !(T5_DIAG & 2)) {

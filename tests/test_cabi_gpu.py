@@ -199,7 +199,8 @@ def test_error_reporting():
 
 
 # ---- the host-buffer path as a persistent plan (rpgp_plan_*; bench.py's e2e) ------------------------------------------------------
-@pytest.mark.parametrize("n,d,J,K,t", [(3000, 10, 20, 1, 11), (700, 6, 5, 1, 3), (2600, 12, 4, 5, 11), (1500, 8, 26, 1, 16)])
+@pytest.mark.parametrize("n,d,J,K,t", [(3000, 10, 20, 1, 11), (700, 6, 5, 1, 3), (2600, 12, 4, 5, 11), (1500, 8, 26, 1, 16), (1200, 7, 5, 1, 20),
+                                       (1030, 5, 40, 1, 2)])
 def test_host_plan_matches_oracle_and_block_shares_sum_to_full(n, d, J, K, t):
     """set_operator (H2D + projection) then kmv (H2D of V, symmetric product, + sigma^2 V, D2H) through the plan handle: the product
     against the FP64 oracle, the one-shot rpgp_kmv_host_f32, and three uneven rank shares summed on the host"""
