@@ -100,7 +100,35 @@ __host__ __device__ __forceinline__ uint32_t sw128_5(uint32_t row, uint32_t kk) 
     return row * 128u + ((((kk >> 2) ^ (row & 7u)) << 4) | ((kk & 3u) << 2));
 }
 
-// tile enumeration shared by all roles: offsets k in [k_begin, k_end), four 32-column tiles per 128-column block
+// threadIdx.x as a value ptxas cannot re-derive from the special register: under register pressure it rematerialises threadIdx-based
+// values with S2R SR_TID inside the hot loops, and S2R queues behind the MUFU.EX2 stream of the sub-partition -- hundreds of clk
+// each in these XU-bound kernels (profiles/tcd_timeline_r02.txt).  A shuffle from the own lane is the identity ptxas does not see
+// through.  Call once, with the whole warp converged.
+__device__ __forceinline__ int opaque_tid() {
+    const int t = (int)threadIdx.x;
+    return __shfl_sync(0xffffffffu, t, t & 31);
+}
+// the same for warp-uniform values derived from special registers (blockIdx, the shared-memory window: S2R SR_CTAID / SR_CgaCtaId)
+__device__ __forceinline__ uint32_t opaque_u32(uint32_t v) { return __shfl_sync(0xffffffffu, v, 0); }
+// barrier operations on 32-bit shared-memory addresses (kept in a register from an opaque base instead of re-derived from a pointer)
+__device__ __forceinline__ void mbar5_wait_a(uint32_t addr, uint32_t parity) {
+    asm volatile(
+        "{\n"
+        ".reg .pred p;\n"
+        "WAIT_LOOP_A:\n"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n"
+        "@p bra WAIT_DONE_A;\n"
+        "bra WAIT_LOOP_A;\n"
+        "WAIT_DONE_A:\n"
+        "}\n" ::"r"(addr),
+        "r"(parity)
+        : "memory");
+}
+__device__ __forceinline__ void mbar5_arrive_a(uint32_t addr) { asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(addr) : "memory"); }
+__device__ __forceinline__ void sts5_v4(uint32_t addr, float4 v) {
+    asm volatile("st.shared.v4.f32 [%0], {%1, %2, %3, %4};" ::"r"(addr), "f"(v.x), "f"(v.y), "f"(v.z), "f"(v.w) : "memory");
+}
+
 // tile enumeration shared by all roles: offsets k in [k_begin, k_end), four 32-column tiles per 128-column block
 struct Tile5Iter {
     int I, B, k_begin, ntiles;

@@ -32,7 +32,8 @@
 //     MMAs either way (40 clk per M128 N32 K8 MMA whatever the number of issuing warps, profiles/umma_rate_r02.txt).  The copy warp
 //     refills a B-image stage as soon as the tile's distance MMAs have completed (ZFREE, committed by the distance issuer), not when
 //     the whole tile is through.
-// TMEM: D1 (row side) 2 x 32 columns, D2 (column side) 2 x 32, D0 (exponents) 2 teams x 3 buffers x 2 groups x 32 = all 512 columns.
+// TMEM: D1 (row side) 2 x 32 columns, D2 (column side) 2 x 32, the A operand of the distance MMAs 128, D0 (exponents) 2 teams x 2
+// buffers x 2 groups x 32 = all 512 columns.  Registers: setmaxnreg gives the arithmetic warps 96, the epilogue and helper warps 48.
 #include <algorithm>
 #include <cstdlib>
 #include <cstring>
@@ -97,11 +98,7 @@ constexpr int BD_BCFULL = 18;    // [1]  bulk copy of the column-side B operand
 constexpr int BD_AFULL = 19;     // [1]  the A image is in tensor memory (count 4: the warps of rows 0..127)
 constexpr int BD_D0FULL = 20;    // [2 teams][D_NBUF]  tcgen05.commit of the team's distance issuer for a batch of two groups
 constexpr int BD_D0FREE = 20 + 2 * D_NBUF;   // [2 teams][D_NBUF]  the team's warps have read the batch (count 8)
-constexpr int BD_XTURN = 30;     // [2]  [T]: the other team has finished the exponentials of a tile (count 8): team T's turn
-static_assert(BD_D0FREE + 2 * D_NBUF <= BD_XTURN, "barrier block is 256 bytes");
-#ifndef TCD_PINGPONG
-#define TCD_PINGPONG 0           // 1 (experiment, 40-60 % SLOWER for 7-8 groups per tile): the exponential phases of the two teams alternate
-#endif
+static_assert(BD_D0FREE + 2 * D_NBUF <= 32, "barrier block is 256 bytes");
 #ifndef TCD_FENCE_ISSUER
 #define TCD_FENCE_ISSUER 0       // 0: every arithmetic warp fences its S stores (generic -> async proxy) before SFULL; 1 (experiment,
 #endif                           // same speed, parity tests pass): one fence by the S-side issuer after it has acquired SFULL
@@ -164,35 +161,62 @@ struct SymDArgs {
     long long n;
     int nblocks, half, nsplits, rb_begin;
     int G, KS, NB, J;            // groups per chunk, k-steps per group, D0 batches (of two groups) per tile, total groups
-    long long* dbg;              // RPGP_TCD_DBG: clock64 stamps of CTA (0,0,0), [64 tiles][8]
+    unsigned* dbg;               // RPGP_TCD_DBG (TCD_DEBUG_STAMPS builds): clock stamps of one CTA, [DBG_NT tiles][DBG_NC]
     int sleep_ns;                // back-off of the helper warps' barrier polls
 };
 
 }  // namespace
 
+// -DTCD_DEBUG_STAMPS: one CTA keeps clock stamps of DBG_NT tiles in shared memory (a store to global memory would sit in front of the
+// arithmetic warps' proxy fence, which waits for it) and copies them out at the end; RPGP_TCD_DBG=1 prints them (launch_sym_tcd).
+// columns: 0 top | 1-4 D0FULL passed, batch k | 5-8 exponentials of batch k issued | 9 TDONE passed | 10 folded | 11 S stores issued |
+// 12 proxy fence done | 13 SFULL arrive || distance issuer: 14-17 batch k issued, 18 ZFULL passed || S-side issuer: 19 waits passed,
+// 20 committed || epilogue: 21 TDONE seen, 22 done
 #ifdef TCD_DEBUG_STAMPS
-#define TCD_STAMP(j, k) do { if (a.dbg && (j) < 64 && blockIdx.x == 7 && blockIdx.y == 0 && blockIdx.z == 0) a.dbg[(j) * 12 + (k)] = clock64(); } while (0)
+constexpr int DBG_T0 = 16, DBG_NT = 40, DBG_NC = 24;
+#define TCD_STAMP(j, k) do { if (stamping && (j) >= DBG_T0 && (j) < DBG_T0 + DBG_NT) dbg_sm[((j) - DBG_T0) * DBG_NC + (k)] = (uint32_t)clock64(); } while (0)
 #else
 #define TCD_STAMP(j, k) do { } while (0)
 #endif
+#ifndef TCD_REGS_ARITH
+#define TCD_REGS_ARITH 96
+#endif
+#ifndef TCD_REGS_EPI
+#define TCD_REGS_EPI 48
+#endif
+#ifndef TCD_REGS_HELP
+#define TCD_REGS_HELP 48
+#endif
+// setmaxnreg moves registers inside the CTA's OWN allocation (768 threads x D_REGS_LAUNCH): a split that needs more than that spins
+// in USETMAXREG.TRY_ALLOC forever (measured the hard way: 104 / 56 / 40 from a launch at 72 hangs)
+constexpr int D_REGS_LAUNCH = 80, D_REGS_ARITH = TCD_REGS_ARITH, D_REGS_EPI = TCD_REGS_EPI, D_REGS_HELP = TCD_REGS_HELP;
+static_assert(16 * D_REGS_ARITH + 4 * D_REGS_EPI + 4 * D_REGS_HELP <= 24 * D_REGS_LAUNCH && 24 * 32 * D_REGS_LAUNCH <= 65536, "register split");
 
 template <int NL>
-__global__ void __maxnreg__(80) mvm_sym_tcd_kernel(const SymDArgs a) {
+__global__ void __maxnreg__(D_REGS_LAUNCH) mvm_sym_tcd_kernel(const SymDArgs a) {
     if (!tcd_gate_open(a.gate, a.gate_max, a.gate_sum4_max)) return;   // coordinates too large for the cancellation in U: sym_tc5.cu's kernel takes the launch
     extern __shared__ unsigned char smem_raw[];
-    const uint32_t base = (smem_u32(smem_raw) + 1023u) & ~1023u;
-    unsigned char* sm = smem_raw + (base - smem_u32(smem_raw));
+    const uint32_t base = opaque_u32((smem_u32(smem_raw) + 1023u) & ~1023u);      // (opaque: see sym_tc_dev.cuh opaque_tid)
+    unsigned char* sm = static_cast<unsigned char*>(__cvta_shared_to_generic((size_t)base));
     uint64_t* bars = reinterpret_cast<uint64_t*>(sm + d_bar(NL));
     uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(sm + d_bar(NL) + 256);
 
-    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
-    const int chunk = blockIdx.z;
+    const int tid = opaque_tid(), warp = tid >> 5, lane = tid & 31;
+    const int bx = (int)opaque_u32(blockIdx.x), by = (int)opaque_u32(blockIdx.y), bz = (int)opaque_u32(blockIdx.z);
+    const uint32_t bar0 = base + d_bar(NL);      // shared-memory address of the barrier block
+#ifdef TCD_DEBUG_STAMPS
+    uint32_t* dbg_sm = reinterpret_cast<uint32_t*>(sm + d_bar(NL) + 512);
+    const bool stamping = a.dbg != nullptr && bx == 7 && by == 0 && bz == 0;
+    if (stamping)
+        for (int q = tid; q < DBG_NT * DBG_NC; q += D_THREADS) dbg_sm[q] = 0u;
+#endif
+    const int chunk = bz;
     Tile5Iter it;
-    it.I = a.rb_begin + blockIdx.x;
+    it.I = a.rb_begin + bx;
     it.B = a.nblocks;
     it.n = a.n;
     const int per = (a.half + a.nsplits - 1) / a.nsplits;
-    it.k_begin = blockIdx.y * per;
+    it.k_begin = by * per;
     it.ntiles = 4 * (min(a.half, it.k_begin + per) - it.k_begin);
     if (it.ntiles < 0) it.ntiles = 0;
     const int G = a.G, KS = a.KS, NB = a.NB;
@@ -214,8 +238,6 @@ __global__ void __maxnreg__(80) mvm_sym_tcd_kernel(const SymDArgs a) {
         }
         mbar_init(&bars[BD_BCFULL], 1);
         mbar_init(&bars[BD_AFULL], 4);
-        mbar_init(&bars[BD_XTURN + 0], D_AW / 2);
-        mbar_init(&bars[BD_XTURN + 1], D_AW / 2);
 #pragma unroll
         for (int s = 0; s < 2 * D_NBUF; ++s) {
             mbar_init(&bars[BD_D0FULL + s], 1);
@@ -234,6 +256,7 @@ __global__ void __maxnreg__(80) mvm_sym_tcd_kernel(const SymDArgs a) {
 
     if (warp < D_AW) {
         // =========================================== arithmetic warps ===================================================
+        asm volatile("setmaxnreg.inc.sync.aligned.u32 %0;" ::"n"(D_REGS_ARITH));
         // two teams of eight warps take the tiles in turn (team = tile parity = S buffer), so that one team's exponentials fill the
         // XU pipe while the other waits for its exponents, loads them, or splits and stores its S tile.  Inside a team: TMEM lane
         // quadrant = warp & 3 (thread = row), half = which 16 of the tile's 32 columns.
@@ -270,7 +293,7 @@ __global__ void __maxnreg__(80) mvm_sym_tcd_kernel(const SymDArgs a) {
             asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory");
             tc5_fence_before();
             __syncwarp();
-            if (lane == 0) mbar5_arrive(&bars[BD_AFULL]);
+            if (lane == 0) mbar5_arrive_a(bar0 + 8u * (uint32_t)(BD_AFULL));
         }
 
         // every warp folds its rows' share (4 of the 16 right-hand sides) of a closed row-side epoch into the running total
@@ -281,7 +304,7 @@ __global__ void __maxnreg__(80) mvm_sym_tcd_kernel(const SymDArgs a) {
             tmem5_ld4(ta + 16u, x);      // Sh.Vl
             tc5_fence_before();
             __syncwarp();
-            if (lane == 0) mbar5_arrive(&bars[BD_D1EMPTY + (e & 1)]);
+            if (elect_one()) mbar5_arrive_a(bar0 + 8u * (uint32_t)(BD_D1EMPTY + (e & 1)));
 #pragma unroll
             for (int q = 0; q < D_FC / 2; ++q) {
                 const f32x2 y = sub2(pack2(d[2 * q] + x[2 * q], d[2 * q + 1] + x[2 * q + 1]), comp[q]);
@@ -291,101 +314,64 @@ __global__ void __maxnreg__(80) mvm_sym_tcd_kernel(const SymDArgs a) {
             }
         };
 
+        int folded = 0;              // row-side epochs folded so far
+        // what follows the exponentials of a tile: wait for the S buffer, fold closed row-side epochs, split and store S, hand it to
+        // the S-side issuer.  (Running this under the first batch of the team's NEXT tile -- sums parked in 16 more registers -- was
+        // measured 15-50 % slower: the two teams run in step, so every warp is in its tail at the same time either way, and the
+        // extra registers spill.  profiles/tcd_variants_r02.txt)
+        auto finish_tile = [&](int pj, const float* sp) {
+            if (pj >= 2) {   // only now is the S buffer needed: tile pj-2 has left the tensor core (its exponentials ran under the S-side
+                            // MMAs of the team's previous tile), and -- the S-side issuer commits in tile order -- every row-side epoch
+                            // that ended at or before tile pj-2 is closed
+                mbar5_wait_a(bar0 + 8u * (uint32_t)(BD_TDONE + team), (uint32_t)(((pj >> 1) - 1) & 1));
+                tc5_fence_after();
+                if (tid == 0 || tid == 256) TCD_STAMP(pj, 9);
+                while ((folded + 1) * D_F <= pj - 1) fold_epoch(folded++);
+            }
+            if (tid == 0 || tid == 256) TCD_STAMP(pj, 10);
+            // split, SWIZZLE_128B_BASE32B (32-byte chunks ^ row % 4), row-local stores (padding rows / columns hold exact zeros:
+            // their exponent is >= D_PAD).  A 16-byte store is served a quarter-warp (8 consecutive rows) at a time and the swizzle
+            // only spreads 4 rows: rows 4..7 of every eight take their two pieces of a 32-byte chunk in the other order, so that the
+            // eight stores of a phase fall on eight different bank quads (in row order they collide two by two)
+            const uint32_t sc = base + D_S + (uint32_t)team * 32768u;
+            const bool sw = ((uint32_t)rtid >> 2) & 1u;
+#pragma unroll
+            for (int pp = 0; pp < 2; ++pp) {
+#pragma unroll
+                for (int i = 0; i < 2; ++i) {
+                    float x[4];
+#pragma unroll
+                    for (int e = 0; e < 4; ++e) x[e] = (sw != (i == 1)) ? sp[8 * pp + 4 + e] : sp[8 * pp + e];
+                    float4 h, l;
+                    h.x = tf32_hi5(x[0]); h.y = tf32_hi5(x[1]); h.z = tf32_hi5(x[2]); h.w = tf32_hi5(x[3]);
+                    l.x = x[0] - h.x; l.y = x[1] - h.y; l.z = x[2] - h.z; l.w = x[3] - h.w;
+                    const uint32_t q1 = (uint32_t)(half * 2 + pp), q0 = (uint32_t)i ^ (uint32_t)sw;      // piece q = 2 q1 + q0
+                    const uint32_t off = (uint32_t)rtid * 128u + (((q1 ^ ((uint32_t)rtid & 3u)) << 5) | (q0 << 4));
+                    sts5_v4(sc + off, h);
+                    sts5_v4(sc + 16384u + off, l);
+                }
+            }
+            if (tid == 0 || tid == 256) TCD_STAMP(pj, 11);
+            if (!TCD_FENCE_ISSUER) fence5_async_smem();
+            if (tid == 0 || tid == 256) TCD_STAMP(pj, 12);
+            __syncwarp();
+            if (elect_one()) mbar5_arrive_a(bar0 + 8u * (uint32_t)(BD_SFULL + team));
+            if (tid == 0 || tid == 256) TCD_STAMP(pj, 13);
+        };
+
         // D0 is handed over in batches of two groups: the team's item i = (tile, batch) lives in the team's D0 buffer i % D_NBUF and
         // is released as soon as its exponents are in registers
-        uint32_t un[32];
-        auto ld_group = [&](uint32_t col, int gb) {
-            asm volatile(
-                "tcgen05.ld.sync.aligned.32x32b.x16.b32 {%0,%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15}, [%16];"
-                : "=r"(un[16 * gb]), "=r"(un[16 * gb + 1]), "=r"(un[16 * gb + 2]), "=r"(un[16 * gb + 3]), "=r"(un[16 * gb + 4]),
-                  "=r"(un[16 * gb + 5]), "=r"(un[16 * gb + 6]), "=r"(un[16 * gb + 7]), "=r"(un[16 * gb + 8]), "=r"(un[16 * gb + 9]),
-                  "=r"(un[16 * gb + 10]), "=r"(un[16 * gb + 11]), "=r"(un[16 * gb + 12]), "=r"(un[16 * gb + 13]), "=r"(un[16 * gb + 14]),
-                  "=r"(un[16 * gb + 15])
-                : "r"(tmem + D_TM_D0 + col + 32u * (uint32_t)gb + (uint32_t)(half * 16) + lanes));
-        };
-        auto ld_wait = [&]() {
-            asm volatile("tcgen05.wait::ld.sync.aligned;"
-                         : "+r"(un[0]), "+r"(un[1]), "+r"(un[2]), "+r"(un[3]), "+r"(un[4]), "+r"(un[5]), "+r"(un[6]), "+r"(un[7]),
-                           "+r"(un[8]), "+r"(un[9]), "+r"(un[10]), "+r"(un[11]), "+r"(un[12]), "+r"(un[13]), "+r"(un[14]), "+r"(un[15]),
-                           "+r"(un[16]), "+r"(un[17]), "+r"(un[18]), "+r"(un[19]), "+r"(un[20]), "+r"(un[21]), "+r"(un[22]), "+r"(un[23]),
-                           "+r"(un[24]), "+r"(un[25]), "+r"(un[26]), "+r"(un[27]), "+r"(un[28]), "+r"(un[29]), "+r"(un[30]), "+r"(un[31])
-                         :
-                         : "memory");
-        };
-#pragma unroll
-        for (int q = 0; q < 32; ++q) un[q] = 0u;
         const uint32_t tbase = tmem + D_TM_D0 + (uint32_t)(half * 16) + lanes;      // this thread's 16 columns of a D0 group
-        int j = 0, folded = 0;       // j counts the live tiles of BOTH teams
+        int j = 0;                   // j counts the live tiles of BOTH teams
         uint32_t item = 0, ibuf = 0, iuse = 0;   // this team's (tile, batch) counter, item % D_NBUF, item / D_NBUF
         for (int t = it.next_live(0); t < it.ntiles; t = it.next_live(t + 1), ++j) {
             if ((j & 1) != team) continue;
-            const int b = team;
-            const long long c0 = it.col0(t) + half * 16;
             const bool diag = it.diag(t);
-            if (tid == 0 || tid == 256) TCD_STAMP(j, 3);
+            const int dcol = diag ? (int)(row - (it.col0(t) + half * 16)) : -1;     // the column of this thread's 16 that is the pair (row, row)
+            if (tid == 0 || tid == 256) TCD_STAMP(j, 0);
             float s[16];
 #pragma unroll
             for (int c = 0; c < 16; ++c) s[c] = 0.f;
-            // exponentials of one group (16 columns of this thread's row) from register slot gb
-            auto exp_group = [&](int gb, int g) {
-                float u[16];
-#pragma unroll
-                for (int c = 0; c < 16; ++c) u[c] = __uint_as_float(un[16 * gb + c]);
-                if (diag) {     // a pair with itself: the exact exponent (no cancellation error on the dominant entries of K)
-                    const int jg = chunk * G + g;
-                    const float nl = jg < a.J ? __ldg(a.nlc + jg) : D_PAD;
-#pragma unroll
-                    for (int c = 0; c < 16; ++c)
-                        if (c0 + c == row) u[c] = nl;
-                }
-#pragma unroll
-                for (int c = 0; c < 16; ++c) s[c] += ex2_ftz(-u[c]);
-            };
-#if TCD_PINGPONG
-            // The exponential phases of the two teams alternate (FlashAttention-3 style ping-pong): a team starts the exponentials of
-            // its tile when the other team has finished those of ITS tile, so that one team's waits, S stores, fences and barrier round
-            // trips run under the other's MUFU work instead of both idling the XU pipe together (the teams otherwise fall into lockstep:
-            // profiles/tcd_variants_r02.txt).  Inside its phase the team runs alone, so the tcgen05.ld of the next group is issued under
-            // the exponentials of the current one (tcgen05.wait::ld waits for ALL outstanding loads: every load is issued right after
-            // the wait for the previous one).
-            {
-                const uint32_t turn = (uint32_t)(j >> 1);       // index of this team's tile
-                if (team == 1) mbar_wait(&bars[BD_XTURN + 1], turn & 1u);
-                else if (turn >= 1) mbar_wait(&bars[BD_XTURN + 0], (turn - 1) & 1u);
-            }
-            uint32_t buf = (uint32_t)(D_NBUF * team) + ibuf;
-            mbar_wait(&bars[BD_D0FULL + buf], iuse & 1u);
-            if (tid == 0 || tid == 256) TCD_STAMP(j, 4);
-            tc5_fence_after();
-            ld_group(64u * buf, 0);
-            for (int k = 0; k < NB; ++k, ++item) {
-                const int g0 = 2 * k, gcnt = min(2, G - g0);
-                ld_wait();                                            // group g0 is in slot 0
-                if (gcnt > 1) ld_group(64u * buf, 1);                 // second group of the batch -> slot 1, under the exponentials of slot 0
-                if (gcnt == 1) {                                      // (single-group last batch: fully read)
-                    tc5_fence_before();
-                    __syncwarp();
-                    if (lane == 0) mbar5_arrive(&bars[BD_D0FREE + buf]);
-                }
-                exp_group(0, g0);
-                if (gcnt > 1) {
-                    ld_wait();                                        // group g0 + 1 is in slot 1: the batch has been read
-                    tc5_fence_before();
-                    __syncwarp();
-                    if (lane == 0) mbar5_arrive(&bars[BD_D0FREE + buf]);
-                }
-                if (++ibuf == D_NBUF) { ibuf = 0; ++iuse; }
-                if (k + 1 < NB) {                                     // first group of the next batch -> slot 0, under the exponentials of slot 1
-                    buf = (uint32_t)(D_NBUF * team) + ibuf;
-                    mbar_wait(&bars[BD_D0FULL + buf], iuse & 1u);
-                    tc5_fence_after();
-                    ld_group(64u * buf, 0);
-                }
-                if (gcnt > 1) exp_group(1, g0 + 1);
-            }
-            __syncwarp();
-            if (lane == 0) mbar5_arrive(&bars[BD_XTURN + (1 - team)]);      // the other team's turn
-#else
             // one batch = two groups: both tcgen05.ld and their wait are ONE asm statement with plain outputs, so that the exponents go
             // from the load's destination registers straight into MUFU.EX2 (the earlier form kept them in an array tied to a separate
             // wait statement and ptxas copied all of them: 17 % of the arithmetic warps' instructions, which run at 83 % of the issue
@@ -394,8 +380,8 @@ __global__ void __maxnreg__(80) mvm_sym_tcd_kernel(const SymDArgs a) {
                 const int g0 = 2 * k;
                 const bool two = g0 + 1 < G;
                 const uint32_t buf = (uint32_t)(D_NBUF * team) + ibuf;
-                mbar_wait(&bars[BD_D0FULL + buf], iuse & 1u);
-                if (k == 0 && (tid == 0 || tid == 256)) TCD_STAMP(j, 4);
+                mbar5_wait_a(bar0 + 8u * (uint32_t)(BD_D0FULL + buf), iuse & 1u);
+                if (tid == 0 || tid == 256) TCD_STAMP(j, 1 + (k & 3));
                 if (++ibuf == D_NBUF) { ibuf = 0; ++iuse; }
                 tc5_fence_after();
                 const uint32_t ta = tbase + 64u * buf;
@@ -422,7 +408,7 @@ __global__ void __maxnreg__(80) mvm_sym_tcd_kernel(const SymDArgs a) {
                 }
                 tc5_fence_before();
                 __syncwarp();
-                if (lane == 0) mbar5_arrive(&bars[BD_D0FREE + buf]);
+                if (elect_one()) mbar5_arrive_a(bar0 + 8u * (uint32_t)(BD_D0FREE + buf));
                 if (diag) {     // a pair with itself: the exact exponent (no cancellation error on the dominant entries of K)
 #pragma unroll
                     for (int gb = 0; gb < 2; ++gb) {
@@ -431,7 +417,7 @@ __global__ void __maxnreg__(80) mvm_sym_tcd_kernel(const SymDArgs a) {
                             const float nl = jg < a.J ? __ldg(a.nlc + jg) : D_PAD;
 #pragma unroll
                             for (int c = 0; c < 16; ++c)
-                                if (c0 + c == row) w[16 * gb + c] = __float_as_uint(nl);
+                                if (c == dcol) w[16 * gb + c] = __float_as_uint(nl);
                         }
                     }
                 }
@@ -441,39 +427,14 @@ __global__ void __maxnreg__(80) mvm_sym_tcd_kernel(const SymDArgs a) {
 #pragma unroll
                     for (int c = 0; c < 16; ++c) s[c] += ex2_ftz(-__uint_as_float(w[16 + c]));
                 }
+                if (tid == 0 || tid == 256) TCD_STAMP(j, 5 + (k & 3));
             }
-#endif
-            if (tid == 0 || tid == 256) TCD_STAMP(j, 1);
-            if (j >= 2) {   // only now is the S buffer needed: tile j-2 has left the tensor core (its exponentials ran under the S-side
-                            // MMAs of the team's previous tile), and -- the S-side issuer commits in tile order -- every row-side epoch
-                            // that ended at or before tile j-2 is closed
-                mbar_wait(&bars[BD_TDONE + b], (uint32_t)(((j >> 1) - 1) & 1));
-                tc5_fence_after();
-                while ((folded + 1) * D_F <= j - 1) fold_epoch(folded++);
-            }
-            if (tid == 0 || tid == 256) TCD_STAMP(j, 0);
-            // split, SWIZZLE_128B_BASE32B (32-byte chunks ^ row % 4), row-local stores (padding rows / columns hold exact zeros:
-            // their exponent is >= D_PAD)
-            unsigned char* sc = sm + D_S + (uint32_t)b * 32768u;
-#pragma unroll
-            for (int qq = 0; qq < 4; ++qq) {
-                const uint32_t q = (uint32_t)(half * 4 + qq);
-                float4 h, l;
-                h.x = tf32_hi5(s[4 * qq]); h.y = tf32_hi5(s[4 * qq + 1]); h.z = tf32_hi5(s[4 * qq + 2]); h.w = tf32_hi5(s[4 * qq + 3]);
-                l.x = s[4 * qq] - h.x; l.y = s[4 * qq + 1] - h.y; l.z = s[4 * qq + 2] - h.z; l.w = s[4 * qq + 3] - h.w;
-                const uint32_t off = (uint32_t)rtid * 128u + ((((q >> 1) ^ ((uint32_t)rtid & 3u)) << 5) | ((q & 1u) << 4));
-                *reinterpret_cast<float4*>(sc + off) = h;
-                *reinterpret_cast<float4*>(sc + 16384u + off) = l;
-            }
-            if (!TCD_FENCE_ISSUER) fence5_async_smem();
-            __syncwarp();
-            if (lane == 0) mbar5_arrive(&bars[BD_SFULL + b]);      // (release: the S-side issuer acquires, then fences the proxies)
-            if (tid == 0 || tid == 256) TCD_STAMP(j, 2);
+            finish_tile(j, s);
         }
         if (j > 0) {    // j = number of live tiles; the row issuer's last commit covers every earlier row-side MMA (the last two
                         // tiles in order: a parity wait must not fall more than one phase behind its barrier)
-            if (j >= 2) mbar_wait(&bars[BD_TDONE + ((j - 2) & 1)], (uint32_t)(((j - 2) >> 1) & 1));
-            mbar_wait(&bars[BD_TDONE + ((j - 1) & 1)], (uint32_t)(((j - 1) >> 1) & 1));
+            if (j >= 2) mbar5_wait_a(bar0 + 8u * (uint32_t)(BD_TDONE + ((j - 2) & 1)), (uint32_t)(((j - 2) >> 1) & 1));
+            mbar5_wait_a(bar0 + 8u * (uint32_t)(BD_TDONE + ((j - 1) & 1)), (uint32_t)(((j - 1) >> 1) & 1));
             tc5_fence_after();
             const int epochs = (j + D_F - 1) / D_F;
             while (folded < epochs) fold_epoch(folded++);
@@ -490,6 +451,7 @@ __global__ void __maxnreg__(80) mvm_sym_tcd_kernel(const SymDArgs a) {
         }
     } else if (warp < D_AW + 4) {
         // =========================================== epilogue warps (column side) ========================================
+        asm volatile("setmaxnreg.dec.sync.aligned.u32 %0;" ::"n"(D_REGS_EPI));
         const int qd = warp - D_AW;                                // TMEM lane quadrant
         int j = 0, jc = 0;
         for (int t = it.next_live(0); t < it.ntiles; t = it.next_live(t + 1), ++j) {
@@ -497,7 +459,7 @@ __global__ void __maxnreg__(80) mvm_sym_tcd_kernel(const SymDArgs a) {
             const bool diag = it.diag(t);
             mbar_wait_ns(a.sleep_ns, &bars[BD_TDONE + b], (uint32_t)((j >> 1) & 1));
             tc5_fence_after();
-            if (qd == 0 && lane == 0) TCD_STAMP(j, 7);
+            if (qd == 0 && lane == 0) TCD_STAMP(j, 21);
             // quadrants 0,1 hold the tf32-part rows of columns 0..15 / 16..31 (lanes 0..15), quadrants 2,3 the remainder rows
             float* P = reinterpret_cast<float*>(sm + D_EPI) + (jc & 1) * 1024;
             if (!diag) {
@@ -527,10 +489,11 @@ __global__ void __maxnreg__(80) mvm_sym_tcd_kernel(const SymDArgs a) {
                 }
                 ++jc;
             }
-            if (qd == 0 && lane == 0) TCD_STAMP(j, 8);
+            if (qd == 0 && lane == 0) TCD_STAMP(j, 22);
         }
     } else {
         // =========================================== helper warps =========================================================
+        asm volatile("setmaxnreg.dec.sync.aligned.u32 %0;" ::"n"(D_REGS_HELP));
         // role 0: S-side MMAs (row side, then column side of every tile); role 1: bulk copies; roles 2, 3: distance MMAs of team 0 / 1.
         // Every lane follows the barriers; tcgen05.mma / commit / cp.async.bulk are issued by one elected lane (elect_one).
         const int role = warp - D_AW - 4;
@@ -548,7 +511,7 @@ __global__ void __maxnreg__(80) mvm_sym_tcd_kernel(const SymDArgs a) {
                 mbar_wait_ns(a.sleep_ns, &bars[BD_SFULL + b], (uint32_t)((j >> 1) & 1));
                 if (TCD_FENCE_ISSUER) fence5_async_smem();     // the team's S stores (acquired through SFULL) -> async proxy (tensor core)
                 tc5_fence_after();
-                if (lane == 0) TCD_STAMP(j, 5);
+                if (lane == 0) TCD_STAMP(j, 19);
                 const bool col_work = !it.diag(t) && !(TCD_DIAG & 2);      // (nothing to do for the column side on the diagonal block)
                 if (elect_one()) {
                     const uint32_t sbuf = base + D_S + (uint32_t)b * 32768u;
@@ -574,7 +537,7 @@ __global__ void __maxnreg__(80) mvm_sym_tcd_kernel(const SymDArgs a) {
                     umma5_commit(&bars[BD_TDONE + b]);
                 }
                 __syncwarp();
-                if (lane == 0) TCD_STAMP(j, 6);
+                if (lane == 0) TCD_STAMP(j, 20);
             }
         } else if (has_tiles && role == 1) {
             // B images D_ZST deep (refilled at ZFREE of the tile that held the stage), B tiles of V D_BST deep (refilled at TDONE)
@@ -633,7 +596,7 @@ __global__ void __maxnreg__(80) mvm_sym_tcd_kernel(const SymDArgs a) {
                 mbar_wait_ns(a.sleep_ns, &bars[BD_ZFULL + zs], (uint32_t)((jd / D_ZST) & 1));
                 if ((jd & 1) != w) continue;
                 tc5_fence_after();
-                if (lane == 0) TCD_STAMP(jd, 9);
+                if (lane == 0) TCD_STAMP(jd, 18);
                 const uint32_t bst = base + d_bimg(NL) + (uint32_t)zs * NL * 8192u;
                 for (int k = 0; k < NB; ++k) {
                     const uint32_t buf = (uint32_t)(D_NBUF * w) + ibuf;
@@ -664,9 +627,9 @@ __global__ void __maxnreg__(80) mvm_sym_tcd_kernel(const SymDArgs a) {
                         if (k == NB - 1) umma5_commit(&bars[BD_ZFREE + zs]);     // the tile's B image has been consumed
                     }
                     __syncwarp();
+                    if (lane == 0) TCD_STAMP(jd, 14 + (k & 3));
                     if (++ibuf == D_NBUF) { ibuf = 0; ++iuse; }
                 }
-                if (lane == 0) TCD_STAMP(jd, 10);
             }
         }
         __syncwarp();
@@ -676,6 +639,10 @@ __global__ void __maxnreg__(80) mvm_sym_tcd_kernel(const SymDArgs a) {
     if (warp == D_AW) {
         asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, 512;" ::"r"(tmem) : "memory");
     }
+#ifdef TCD_DEBUG_STAMPS
+    if (stamping)
+        for (int q = tid; q < DBG_NT * DBG_NC; q += D_THREADS) reinterpret_cast<uint32_t*>(a.dbg)[q] = dbg_sm[q];
+#endif
 }
 
 // ---- operand images ---------------------------------------------------------------------------------------------------------
@@ -869,9 +836,12 @@ int launch_sym_tcd(const float* zp, long long n, const Layout& lay, const float*
 #ifdef TCD_DEBUG_STAMPS
     static const int dbg_env = [] { const char* e = getenv("RPGP_TCD_DBG"); return e ? atoi(e) : 0; }();
     if (dbg_env) {
-        RPGP_CUDA_OK(cudaMalloc(&a.dbg, 64 * 12 * sizeof(long long)));
-        RPGP_CUDA_OK(cudaMemset(a.dbg, 0, 64 * 12 * sizeof(long long)));
+        RPGP_CUDA_OK(cudaMalloc(&a.dbg, DBG_NT * DBG_NC * sizeof(unsigned)));
+        RPGP_CUDA_OK(cudaMemset(a.dbg, 0, DBG_NT * DBG_NC * sizeof(unsigned)));
     }
+    const size_t dbg_smem = 4096;
+#else
+    const size_t dbg_smem = 0;
 #endif
     static const int splits_env = [] { const char* e = getenv("RPGP_SYM_SPLITS"); return e ? atoi(e) : 0; }();
     long long want = pick_splits((long long)nrb * p.nchunks, a.half, 148);      // one CTA per SM
@@ -881,29 +851,35 @@ int launch_sym_tcd(const float* zp, long long n, const Layout& lay, const float*
     dim3 grid((unsigned)nrb, (unsigned)a.nsplits, (unsigned)p.nchunks);
     cudaError_t e;
     if (p.NL == 1) {
-        e = cudaFuncSetAttribute(mvm_sym_tcd_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)d_smem_bytes(1));
+        e = cudaFuncSetAttribute(mvm_sym_tcd_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(d_smem_bytes(1) + dbg_smem));
         if (e != cudaSuccess) return cuda_fail(e, "cudaFuncSetAttribute(mvm_sym_tcd_kernel<1>)");
-        mvm_sym_tcd_kernel<1><<<grid, D_THREADS, d_smem_bytes(1), st>>>(a);
+        mvm_sym_tcd_kernel<1><<<grid, D_THREADS, d_smem_bytes(1) + dbg_smem, st>>>(a);
     } else {
-        e = cudaFuncSetAttribute(mvm_sym_tcd_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)d_smem_bytes(2));
+        e = cudaFuncSetAttribute(mvm_sym_tcd_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(d_smem_bytes(2) + dbg_smem));
         if (e != cudaSuccess) return cuda_fail(e, "cudaFuncSetAttribute(mvm_sym_tcd_kernel<2>)");
-        mvm_sym_tcd_kernel<2><<<grid, D_THREADS, d_smem_bytes(2), st>>>(a);
+        mvm_sym_tcd_kernel<2><<<grid, D_THREADS, d_smem_bytes(2) + dbg_smem, st>>>(a);
     }
     note_launch();
     *gate_out = gate;
 #ifdef TCD_DEBUG_STAMPS
-    if (a.dbg) {   // debugging aid only: synchronises and prints the stamps relative to the first one
-        long long h[64 * 12];
+    if (a.dbg) {   // debugging aid only: synchronises and prints the stamps relative to the first stamped tile's top
+        static unsigned h[DBG_NT * DBG_NC];
         RPGP_CUDA_OK(cudaStreamSynchronize(st));
         RPGP_CUDA_OK(cudaMemcpy(h, a.dbg, sizeof(h), cudaMemcpyDeviceToHost));
         cudaFree(a.dbg);
-        fprintf(stderr, "clk relative to tile 16's loop top; team = tile parity\n"
-                        "tile |  top  TDONEok D0FULL expdone SFULL | dist: Zfull issued | row: Sfull commit | col commit | epi: TDONE done\n");
-        const long long o = h[16 * 12 + 3];
-        for (int j = 16; j < 44; ++j) {
-            auto r = [&](int k) { return h[j * 12 + k] ? h[j * 12 + k] - o : -1; };
-            fprintf(stderr, "%3d  | %6lld %6lld %6lld %6lld %6lld | %6lld %6lld | %6lld %6lld | %6lld | %6lld %6lld\n", j, r(3), r(0), r(4), r(1), r(2), r(9), r(10), r(5),
-                    r(6), r(11), r(7), r(8));
+        fprintf(stderr, "clk relative to the first stamped tile's top; team = tile parity\n"
+                        "tile |   top | D0FULL passed b0..b3      | exps issued b0..b3        |  TDONE   fold stores  fence arrive |"
+                        " dist: ZFULL, issued b0..b3        | S: ready commit | epi: TDONE  done\n");
+        const unsigned o = h[0];
+        for (int r = 0; r < DBG_NT; ++r) {
+            fprintf(stderr, "%3d  |", DBG_T0 + r);
+            const int order[23] = {0, 1, 2, 3, 4, 5, 6, 7, 8, 9, 10, 11, 12, 13, 18, 14, 15, 16, 17, 19, 20, 21, 22};
+            for (int q = 0; q < 23; ++q) {
+                const unsigned v = h[r * DBG_NC + order[q]];
+                if (v) fprintf(stderr, " %6d", (int)(v - o)); else fprintf(stderr, "     -1");
+                if (q == 0 || q == 4 || q == 8 || q == 13 || q == 18 || q == 20) fprintf(stderr, " |");
+            }
+            fprintf(stderr, "\n");
         }
     }
 #endif

@@ -501,7 +501,8 @@ class AddedDiagLazyTensor(LazyTensor):
         s = _settings()
         with torch.no_grad():
             if self._use_cholesky():
-                Lc = torch.linalg.cholesky(self.evaluate().detach())
+                from .solver.inv_quad_logdet import psd_safe_cholesky
+                Lc = psd_safe_cholesky(self.evaluate().detach())
                 return torch.cholesky_solve(rhs if rhs.dim() > 1 else rhs.unsqueeze(-1), Lc).reshape(rhs.shape)
             return self._solve(rhs, self._preconditioner(), tolerance=s.eval_cg_tolerance.value())
 

@@ -90,6 +90,26 @@ class _InvQuadLogDetCG(torch.autograd.Function):
         return (None, None, rhs_grad) + grads
 
 
+def psd_safe_cholesky(A, max_tries=3):
+    """Cholesky factor of A; when the factorisation fails, retried with a diagonal jitter of 1e-6 (1e-8 in FP64) times 1, 10, 100.
+    GPyTorch's `psd_safe_cholesky` (gpytorch/utils/cholesky.py, the routine behind every dense root of the reference's models):
+    a predictive covariance assembled from CG solves at eval_cg_tolerance can miss positive definiteness by rounding."""
+    try:
+        return torch.linalg.cholesky(A)
+    except RuntimeError as err:
+        if torch.isnan(A).any():
+            raise
+        first = err
+    jitter = 1e-6 if A.dtype == torch.float32 else 1e-8
+    eye = torch.eye(A.shape[-1], dtype=A.dtype, device=A.device)
+    for i in range(max_tries):
+        try:
+            return torch.linalg.cholesky(A + (jitter * 10.0 ** i) * eye)
+        except RuntimeError:
+            continue
+    raise first
+
+
 def inv_quad_logdet(op, inv_quad_rhs=None, logdet=False):
     """op: AddedDiagLazyTensor (K + sigma^2 I).  Returns (inv_quad, logdet) as 0-dim tensors (None when not asked)."""
     n = op.shape[-1]
@@ -99,7 +119,7 @@ def inv_quad_logdet(op, inv_quad_rhs=None, logdet=False):
         rhs = inv_quad_rhs.unsqueeze(-1) if inv_quad_rhs.dim() == 1 else inv_quad_rhs
     if op._use_cholesky():
         Kd = op.evaluate()
-        Lc = torch.linalg.cholesky(Kd)
+        Lc = psd_safe_cholesky(Kd)
         iq = None
         if inv_quad_rhs is not None:
             sol = torch.linalg.solve_triangular(Lc, rhs, upper=False)

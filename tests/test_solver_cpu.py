@@ -128,6 +128,25 @@ def test_inv_quad_logdet_cholesky_path_is_exact():
     np.testing.assert_allclose(float(noise.grad), np.trace(Kinv) - alpha @ alpha, rtol=1e-8)
 
 
+def test_psd_safe_cholesky_retries_with_jitter_like_gpytorch():
+    from rpgp.solver.inv_quad_logdet import psd_safe_cholesky
+    g = torch.Generator().manual_seed(0)
+    B = torch.randn(40, 6, generator=g)
+    A = B @ B.T                                              # rank 6: plain Cholesky fails
+    with pytest.raises(RuntimeError):
+        torch.linalg.cholesky(A - 1e-7 * torch.eye(40))
+    L = psd_safe_cholesky(A - 1e-7 * torch.eye(40))
+    assert torch.isfinite(L).all() and float((L @ L.T - A).abs().max()) < 1e-3
+    good = A + torch.eye(40)
+    assert torch.equal(psd_safe_cholesky(good), torch.linalg.cholesky(good))      # untouched when the matrix factors
+    with pytest.raises(RuntimeError):
+        psd_safe_cholesky(A - 10.0 * torch.eye(40))           # far from positive definite: the original error comes back
+    bad = A.clone()
+    bad[0, 0] = float("nan")
+    with pytest.raises(RuntimeError):
+        psd_safe_cholesky(bad)
+
+
 def test_settings_context_managers_nest_and_restore():
     assert settings.cg_tolerance.value() == 1.0 and settings.eval_cg_tolerance.value() == 0.01
     assert settings.max_cg_iterations.value() == 1000 and settings.max_cholesky_size.value() == 800
