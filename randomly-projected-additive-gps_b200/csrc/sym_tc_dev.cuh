@@ -108,8 +108,13 @@ __device__ __forceinline__ int opaque_tid() {
     const int t = (int)threadIdx.x;
     return __shfl_sync(0xffffffffu, t, t & 31);
 }
-// the same for warp-uniform values derived from special registers (blockIdx, the shared-memory window: S2R SR_CTAID / SR_CgaCtaId)
-__device__ __forceinline__ uint32_t opaque_u32(uint32_t v) { return __shfl_sync(0xffffffffu, v, 0); }
+// the same for warp-uniform values (blockIdx, the shared-memory window: S2R SR_CTAID / SR_CgaCtaId; kernel parameters: LDC).  The
+// shuffle is written in PTX: the compiler folds __shfl_sync of a value it knows to be uniform.
+__device__ __forceinline__ uint32_t opaque_u32(uint32_t v) {
+    uint32_t r;
+    asm volatile("shfl.sync.idx.b32 %0, %1, 0, 0x1f, 0xffffffff;" : "=r"(r) : "r"(v));
+    return r;
+}
 // barrier operations on 32-bit shared-memory addresses (kept in a register from an opaque base instead of re-derived from a pointer)
 __device__ __forceinline__ void mbar5_wait_a(uint32_t addr, uint32_t parity) {
     asm volatile(
@@ -124,12 +129,20 @@ __device__ __forceinline__ void mbar5_wait_a(uint32_t addr, uint32_t parity) {
         "r"(parity)
         : "memory");
 }
+// a value read back from shared memory with a volatile load: the only form of a kernel parameter that ptxas will not reload from
+// the constant bank (it folds even a shuffle of a uniform value)
+__device__ __forceinline__ uint32_t lds5_volatile(uint32_t addr) {
+    uint32_t r;
+    asm volatile("ld.volatile.shared.u32 %0, [%1];" : "=r"(r) : "r"(addr) : "memory");
+    return r;
+}
 __device__ __forceinline__ void mbar5_arrive_a(uint32_t addr) { asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(addr) : "memory"); }
 __device__ __forceinline__ void sts5_v4(uint32_t addr, float4 v) {
     asm volatile("st.shared.v4.f32 [%0], {%1, %2, %3, %4};" ::"r"(addr), "f"(v.x), "f"(v.y), "f"(v.z), "f"(v.w) : "memory");
 }
 
 // tile enumeration shared by all roles: offsets k in [k_begin, k_end), four 32-column tiles per 128-column block
+struct LiveRun { int t, lim; };      // [t, lim): consecutive live tiles inside one 128-column block (t == ntiles: no tile left)
 struct Tile5Iter {
     int I, B, k_begin, ntiles;
     long long n;
@@ -137,8 +150,26 @@ struct Tile5Iter {
     __device__ __forceinline__ bool offset_active(int k) const { return !((B % 2 == 0) && (k == B / 2) && (I >= B / 2)); }
     __device__ __forceinline__ long long col0(int t) const { return (long long)block_of(k_begin + (t >> 2)) * T5_ROWS + (t & 3) * T5_BN; }
     __device__ __forceinline__ bool live(int t) const { return offset_active(k_begin + (t >> 2)) && col0(t) < n; }
-    __device__ __forceinline__ bool diag(int t) const { return block_of(k_begin + (t >> 2)) == I; }
+    // (offsets k stay below B: half = B / 2 + 1 <= B, so block_of(k) == I exactly when k == 0)
+    __device__ __forceinline__ bool diag(int t) const { return k_begin + (t >> 2) == 0; }
     __device__ __forceinline__ int next_live(int t) const { while (t < ntiles && !live(t)) ++t; return t; }
+    // the same enumeration with the liveness test paid once per block instead of once per tile (a tile's neighbours in its block
+    // are live up to the first column >= n): advance() is an increment and a compare for three tiles out of four
+    __device__ __forceinline__ LiveRun run_from(int t) const {
+        LiveRun r;
+        r.t = next_live(t);
+        r.lim = r.t;
+        if (r.t < ntiles) {
+            const int blk_end = min(ntiles, (r.t | 3) + 1);
+            r.lim = r.t + 1;
+            while (r.lim < blk_end && live(r.lim)) ++r.lim;
+        }
+        return r;
+    }
+    __device__ __forceinline__ LiveRun first_run() const { return run_from(0); }
+    __device__ __forceinline__ void advance(LiveRun& r) const {
+        if (++r.t >= r.lim) r = run_from(r.t);
+    }
 };
 
 // gate of the distance-on-tensor-core path: words written by its pre-pass = {bits of max r2, -, double sum of r2^2} where r2 is

@@ -37,6 +37,7 @@
 #include <algorithm>
 #include <cstdlib>
 #include <cstring>
+#include <type_traits>
 
 #include "aux_kernels.cuh"
 #include "sym_tc.cuh"
@@ -219,7 +220,8 @@ __global__ void __maxnreg__(D_REGS_LAUNCH) mvm_sym_tcd_kernel(const SymDArgs a) 
     it.k_begin = by * per;
     it.ntiles = 4 * (min(a.half, it.k_begin + per) - it.k_begin);
     if (it.ntiles < 0) it.ntiles = 0;
-    const int G = a.G, KS = a.KS, NB = a.NB;
+    int G = a.G, NB = a.NB;
+    const int KS = a.KS;
 
     if (tid == 0) {
 #pragma unroll
@@ -244,6 +246,9 @@ __global__ void __maxnreg__(D_REGS_LAUNCH) mvm_sym_tcd_kernel(const SymDArgs a) 
             mbar_init(&bars[BD_D0FREE + s], D_AW / 2);
         }
         mbar_fence_init();
+        // loop parameters, to be read back as register values (see below)
+        uint32_t* pb = reinterpret_cast<uint32_t*>(sm + d_bar(NL) + 264);
+        pb[0] = (uint32_t)G; pb[1] = (uint32_t)NB; pb[2] = (uint32_t)it.B; pb[3] = (uint32_t)it.I; pb[4] = (uint32_t)it.k_begin; pb[5] = (uint32_t)it.ntiles;
     }
     if (warp == D_AW) {
         asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], 512;" ::"r"(smem_u32(tmem_slot)) : "memory");
@@ -253,6 +258,14 @@ __global__ void __maxnreg__(D_REGS_LAUNCH) mvm_sym_tcd_kernel(const SymDArgs a) 
     __syncthreads();
     tc5_fence_after();
     const uint32_t tmem = *tmem_slot;
+    // the parameters the loops test on every tile / batch come back from shared memory through volatile loads: ptxas reloads plain
+    // kernel parameters from the constant bank at every use, and an LDC followed at once by the compare and branch that need it costs
+    // its full latency -- the arithmetic warps' tile top had four of those in a row (profiles/tcd_timeline_r02.txt)
+    {
+        const uint32_t pa = bar0 + 264u;
+        G = (int)lds5_volatile(pa); NB = (int)lds5_volatile(pa + 4u); it.B = (int)lds5_volatile(pa + 8u); it.I = (int)lds5_volatile(pa + 12u);
+        it.k_begin = (int)lds5_volatile(pa + 16u); it.ntiles = (int)lds5_volatile(pa + 20u);
+    }
 
     if (warp < D_AW) {
         // =========================================== arithmetic warps ===================================================
@@ -359,32 +372,27 @@ __global__ void __maxnreg__(D_REGS_LAUNCH) mvm_sym_tcd_kernel(const SymDArgs a) 
             if (tid == 0 || tid == 256) TCD_STAMP(pj, 13);
         };
 
-        // D0 is handed over in batches of two groups: the team's item i = (tile, batch) lives in the team's D0 buffer i % D_NBUF and
-        // is released as soon as its exponents are in registers
-        const uint32_t tbase = tmem + D_TM_D0 + (uint32_t)(half * 16) + lanes;      // this thread's 16 columns of a D0 group
-        int j = 0;                   // j counts the live tiles of BOTH teams
-        uint32_t item = 0, ibuf = 0, iuse = 0;   // this team's (tile, batch) counter, item % D_NBUF, item / D_NBUF
-        for (int t = it.next_live(0); t < it.ntiles; t = it.next_live(t + 1), ++j) {
-            if ((j & 1) != team) continue;
-            const bool diag = it.diag(t);
-            const int dcol = diag ? (int)(row - (it.col0(t) + half * 16)) : -1;     // the column of this thread's 16 that is the pair (row, row)
-            if (tid == 0 || tid == 256) TCD_STAMP(j, 0);
-            float s[16];
-#pragma unroll
-            for (int c = 0; c < 16; ++c) s[c] = 0.f;
+        // D0 is handed over in batches of two groups: the team's item i = (tile, batch) lives in the team's D0 buffer i % 2 and is
+        // released as soon as its exponents are in registers.  The hand-off sits on every warp's critical path (the teams run in
+        // step, nothing hides it: 25 % of the arithmetic warps' time in profiles/ncu_r02b_tcd_cfg5b_summary.md), so its state is a
+        // handful of precomputed addresses that toggle, and the diagonal block's exact-exponent fix lives in a second copy of the loop.
+        static_assert(D_NBUF == 2, "the toggling below assumes two D0 buffers per team");
+        const uint32_t tteam = tmem + D_TM_D0 + (uint32_t)(half * 16) + lanes + 64u * (uint32_t)(D_NBUF * team);   // + 64 ibuf: this thread's 16 columns
+        const uint32_t full0 = bar0 + 8u * (uint32_t)(BD_D0FULL + D_NBUF * team), free0 = bar0 + 8u * (uint32_t)(BD_D0FREE + D_NBUF * team);
+        uint32_t ibuf = 0, par = 0;      // buffer of the next batch, parity of its D0FULL phase
+        float s[16];
+        int dcol = -1;                   // diagonal block: the column of this thread's 16 that is the pair (row, row)
+        int jcur = 0;
+        auto run_batches = [&](auto diag_tag) {
+            constexpr bool DIAG = decltype(diag_tag)::value;
             // one batch = two groups: both tcgen05.ld and their wait are ONE asm statement with plain outputs, so that the exponents go
-            // from the load's destination registers straight into MUFU.EX2 (the earlier form kept them in an array tied to a separate
-            // wait statement and ptxas copied all of them: 17 % of the arithmetic warps' instructions, which run at 83 % of the issue
-            // budget of the XU-bound tile -- profiles/ncu_r02_tcd_cfg5b_summary.md)
-            for (int k = 0; k < NB; ++k, ++item) {
-                const int g0 = 2 * k;
-                const bool two = g0 + 1 < G;
-                const uint32_t buf = (uint32_t)(D_NBUF * team) + ibuf;
-                mbar5_wait_a(bar0 + 8u * (uint32_t)(BD_D0FULL + buf), iuse & 1u);
-                if (tid == 0 || tid == 256) TCD_STAMP(j, 1 + (k & 3));
-                if (++ibuf == D_NBUF) { ibuf = 0; ++iuse; }
+            // from the load's destination registers straight into MUFU.EX2
+            for (int k = 0; k < NB; ++k) {
+                const bool two = 2 * k + 1 < G;
+                mbar5_wait_a(full0 + 8u * ibuf, par);
+                if (tid == 0 || tid == 256) TCD_STAMP(jcur, 1 + (k & 3));
                 tc5_fence_after();
-                const uint32_t ta = tbase + 64u * buf;
+                const uint32_t ta = tteam + 64u * ibuf;
                 uint32_t w[32];
                 if (two) {
                     asm volatile(
@@ -408,12 +416,14 @@ __global__ void __maxnreg__(D_REGS_LAUNCH) mvm_sym_tcd_kernel(const SymDArgs a) 
                 }
                 tc5_fence_before();
                 __syncwarp();
-                if (elect_one()) mbar5_arrive_a(bar0 + 8u * (uint32_t)(BD_D0FREE + buf));
-                if (diag) {     // a pair with itself: the exact exponent (no cancellation error on the dominant entries of K)
+                if (elect_one()) mbar5_arrive_a(free0 + 8u * ibuf);
+                par ^= ibuf;            // the phase advances when the buffer index wraps (1 -> 0)
+                ibuf ^= 1u;
+                if constexpr (DIAG) {   // a pair with itself: the exact exponent (no cancellation error on the dominant entries of K)
 #pragma unroll
                     for (int gb = 0; gb < 2; ++gb) {
                         if (gb == 0 || two) {
-                            const int jg = chunk * G + g0 + gb;
+                            const int jg = chunk * G + 2 * k + gb;
                             const float nl = jg < a.J ? __ldg(a.nlc + jg) : D_PAD;
 #pragma unroll
                             for (int c = 0; c < 16; ++c)
@@ -427,7 +437,25 @@ __global__ void __maxnreg__(D_REGS_LAUNCH) mvm_sym_tcd_kernel(const SymDArgs a) 
 #pragma unroll
                     for (int c = 0; c < 16; ++c) s[c] += ex2_ftz(-__uint_as_float(w[16 + c]));
                 }
-                if (tid == 0 || tid == 256) TCD_STAMP(j, 5 + (k & 3));
+                if (tid == 0 || tid == 256) TCD_STAMP(jcur, 5 + (k & 3));
+            }
+        };
+
+        int j = 0;                   // j counts the live tiles of BOTH teams
+        LiveRun run = it.first_run();
+        for (; run.t < it.ntiles; it.advance(run), ++j) {
+            if ((j & 1) != team) continue;
+            const int t = run.t;
+            const bool diag = it.diag(t);
+            jcur = j;
+            if (tid == 0 || tid == 256) TCD_STAMP(j, 0);
+#pragma unroll
+            for (int c = 0; c < 16; ++c) s[c] = 0.f;
+            if (diag) {
+                dcol = (int)(row - (it.col0(t) + half * 16));
+                run_batches(std::true_type{});
+            } else {
+                run_batches(std::false_type{});
             }
             finish_tile(j, s);
         }
