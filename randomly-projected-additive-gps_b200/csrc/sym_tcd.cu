@@ -343,23 +343,37 @@ __global__ void __maxnreg__(D_REGS_LAUNCH) mvm_sym_tcd_kernel(const SymDArgs a) 
             }
             if (tid == 0 || tid == 256) TCD_STAMP(pj, 10);
             // split, SWIZZLE_128B_BASE32B (32-byte chunks ^ row % 4), row-local stores (padding rows / columns hold exact zeros:
-            // their exponent is >= D_PAD).  A 16-byte store is served a quarter-warp (8 consecutive rows) at a time and the swizzle
-            // only spreads 4 rows: rows 4..7 of every eight take their two pieces of a 32-byte chunk in the other order, so that the
-            // eight stores of a phase fall on eight different bank quads (in row order they collide two by two)
+            // their exponent is >= D_PAD).  In row order a quarter-warp's eight 16-byte stores collide two by two (the swizzle only
+            // spreads 4 rows); letting rows 4..7 of every eight store the halves of a 32-byte chunk in the other order removes the
+            // conflicts at the price of 16 selects.  That pays when a tile is little more than its stores (one or two groups per
+            // chunk: -9 %) and costs 1-2 % otherwise (profiles/tcd_timeline_r02.txt), hence the two forms.
             const uint32_t sc = base + D_S + (uint32_t)team * 32768u;
-            const bool sw = ((uint32_t)rtid >> 2) & 1u;
+            if (G <= 2) {
+                const bool sw = ((uint32_t)rtid >> 2) & 1u;
 #pragma unroll
-            for (int pp = 0; pp < 2; ++pp) {
+                for (int pp = 0; pp < 2; ++pp) {
 #pragma unroll
-                for (int i = 0; i < 2; ++i) {
-                    float x[4];
+                    for (int i = 0; i < 2; ++i) {
+                        float x[4];
 #pragma unroll
-                    for (int e = 0; e < 4; ++e) x[e] = (sw != (i == 1)) ? sp[8 * pp + 4 + e] : sp[8 * pp + e];
+                        for (int e = 0; e < 4; ++e) x[e] = (sw != (i == 1)) ? sp[8 * pp + 4 + e] : sp[8 * pp + e];
+                        float4 h, l;
+                        h.x = tf32_hi5(x[0]); h.y = tf32_hi5(x[1]); h.z = tf32_hi5(x[2]); h.w = tf32_hi5(x[3]);
+                        l.x = x[0] - h.x; l.y = x[1] - h.y; l.z = x[2] - h.z; l.w = x[3] - h.w;
+                        const uint32_t q1 = (uint32_t)(half * 2 + pp), q0 = (uint32_t)i ^ (uint32_t)sw;      // piece q = 2 q1 + q0
+                        const uint32_t off = (uint32_t)rtid * 128u + (((q1 ^ ((uint32_t)rtid & 3u)) << 5) | (q0 << 4));
+                        sts5_v4(sc + off, h);
+                        sts5_v4(sc + 16384u + off, l);
+                    }
+                }
+            } else {
+#pragma unroll
+                for (int qq = 0; qq < 4; ++qq) {
+                    const uint32_t q = (uint32_t)(half * 4 + qq);
                     float4 h, l;
-                    h.x = tf32_hi5(x[0]); h.y = tf32_hi5(x[1]); h.z = tf32_hi5(x[2]); h.w = tf32_hi5(x[3]);
-                    l.x = x[0] - h.x; l.y = x[1] - h.y; l.z = x[2] - h.z; l.w = x[3] - h.w;
-                    const uint32_t q1 = (uint32_t)(half * 2 + pp), q0 = (uint32_t)i ^ (uint32_t)sw;      // piece q = 2 q1 + q0
-                    const uint32_t off = (uint32_t)rtid * 128u + (((q1 ^ ((uint32_t)rtid & 3u)) << 5) | (q0 << 4));
+                    h.x = tf32_hi5(sp[4 * qq]); h.y = tf32_hi5(sp[4 * qq + 1]); h.z = tf32_hi5(sp[4 * qq + 2]); h.w = tf32_hi5(sp[4 * qq + 3]);
+                    l.x = sp[4 * qq] - h.x; l.y = sp[4 * qq + 1] - h.y; l.z = sp[4 * qq + 2] - h.z; l.w = sp[4 * qq + 3] - h.w;
+                    const uint32_t off = (uint32_t)rtid * 128u + ((((q >> 1) ^ ((uint32_t)rtid & 3u)) << 5) | ((q & 1u) << 4));
                     sts5_v4(sc + off, h);
                     sts5_v4(sc + 16384u + off, l);
                 }
@@ -383,62 +397,63 @@ __global__ void __maxnreg__(D_REGS_LAUNCH) mvm_sym_tcd_kernel(const SymDArgs a) 
         float s[16];
         int dcol = -1;                   // diagonal block: the column of this thread's 16 that is the pair (row, row)
         int jcur = 0;
-        auto run_batches = [&](auto diag_tag) {
-            constexpr bool DIAG = decltype(diag_tag)::value;
-            // one batch = two groups: both tcgen05.ld and their wait are ONE asm statement with plain outputs, so that the exponents go
-            // from the load's destination registers straight into MUFU.EX2
-            for (int k = 0; k < NB; ++k) {
-                const bool two = 2 * k + 1 < G;
-                mbar5_wait_a(full0 + 8u * ibuf, par);
-                if (tid == 0 || tid == 256) TCD_STAMP(jcur, 1 + (k & 3));
-                tc5_fence_after();
-                const uint32_t ta = tteam + 64u * ibuf;
-                uint32_t w[32];
-                if (two) {
-                    asm volatile(
-                        "tcgen05.ld.sync.aligned.32x32b.x16.b32 {%0,%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15}, [%32];\n\t"
-                        "tcgen05.ld.sync.aligned.32x32b.x16.b32 {%16,%17,%18,%19,%20,%21,%22,%23,%24,%25,%26,%27,%28,%29,%30,%31}, [%33];\n\t"
-                        "tcgen05.wait::ld.sync.aligned;"
-                        : "=r"(w[0]), "=r"(w[1]), "=r"(w[2]), "=r"(w[3]), "=r"(w[4]), "=r"(w[5]), "=r"(w[6]), "=r"(w[7]), "=r"(w[8]), "=r"(w[9]),
-                          "=r"(w[10]), "=r"(w[11]), "=r"(w[12]), "=r"(w[13]), "=r"(w[14]), "=r"(w[15]), "=r"(w[16]), "=r"(w[17]), "=r"(w[18]),
-                          "=r"(w[19]), "=r"(w[20]), "=r"(w[21]), "=r"(w[22]), "=r"(w[23]), "=r"(w[24]), "=r"(w[25]), "=r"(w[26]), "=r"(w[27]),
-                          "=r"(w[28]), "=r"(w[29]), "=r"(w[30]), "=r"(w[31])
-                        : "r"(ta), "r"(ta + 32u)
-                        : "memory");
-                } else {
-                    asm volatile(
-                        "tcgen05.ld.sync.aligned.32x32b.x16.b32 {%0,%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15}, [%16];\n\t"
-                        "tcgen05.wait::ld.sync.aligned;"
-                        : "=r"(w[0]), "=r"(w[1]), "=r"(w[2]), "=r"(w[3]), "=r"(w[4]), "=r"(w[5]), "=r"(w[6]), "=r"(w[7]), "=r"(w[8]), "=r"(w[9]),
-                          "=r"(w[10]), "=r"(w[11]), "=r"(w[12]), "=r"(w[13]), "=r"(w[14]), "=r"(w[15])
-                        : "r"(ta)
-                        : "memory");
-                }
-                tc5_fence_before();
-                __syncwarp();
-                if (elect_one()) mbar5_arrive_a(free0 + 8u * ibuf);
-                par ^= ibuf;            // the phase advances when the buffer index wraps (1 -> 0)
-                ibuf ^= 1u;
-                if constexpr (DIAG) {   // a pair with itself: the exact exponent (no cancellation error on the dominant entries of K)
-#pragma unroll
-                    for (int gb = 0; gb < 2; ++gb) {
-                        if (gb == 0 || two) {
-                            const int jg = chunk * G + 2 * k + gb;
-                            const float nl = jg < a.J ? __ldg(a.nlc + jg) : D_PAD;
-#pragma unroll
-                            for (int c = 0; c < 16; ++c)
-                                if (c == dcol) w[16 * gb + c] = __float_as_uint(nl);
-                        }
-                    }
-                }
-#pragma unroll
-                for (int c = 0; c < 16; ++c) s[c] += ex2_ftz(-__uint_as_float(w[c]));
-                if (two) {
-#pragma unroll
-                    for (int c = 0; c < 16; ++c) s[c] += ex2_ftz(-__uint_as_float(w[16 + c]));
-                }
-                if (tid == 0 || tid == 256) TCD_STAMP(jcur, 5 + (k & 3));
+        // one batch = two groups (the last one of a chunk with an odd number of groups: one): both tcgen05.ld and their wait are ONE
+        // asm statement with plain outputs, so that the exponents go from the load's destination registers straight into MUFU.EX2
+        auto one_batch = [&](auto diag_tag, auto two_tag, int k) {
+            constexpr bool DIAG = decltype(diag_tag)::value, TWO = decltype(two_tag)::value;
+            mbar5_wait_a(full0 + 8u * ibuf, par);
+            if (tid == 0 || tid == 256) TCD_STAMP(jcur, 1 + (k & 3));
+            tc5_fence_after();
+            const uint32_t ta = tteam + 64u * ibuf;
+            uint32_t w[32];
+            if constexpr (TWO) {
+                asm volatile(
+                    "tcgen05.ld.sync.aligned.32x32b.x16.b32 {%0,%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15}, [%32];\n\t"
+                    "tcgen05.ld.sync.aligned.32x32b.x16.b32 {%16,%17,%18,%19,%20,%21,%22,%23,%24,%25,%26,%27,%28,%29,%30,%31}, [%33];\n\t"
+                    "tcgen05.wait::ld.sync.aligned;"
+                    : "=r"(w[0]), "=r"(w[1]), "=r"(w[2]), "=r"(w[3]), "=r"(w[4]), "=r"(w[5]), "=r"(w[6]), "=r"(w[7]), "=r"(w[8]), "=r"(w[9]),
+                      "=r"(w[10]), "=r"(w[11]), "=r"(w[12]), "=r"(w[13]), "=r"(w[14]), "=r"(w[15]), "=r"(w[16]), "=r"(w[17]), "=r"(w[18]),
+                      "=r"(w[19]), "=r"(w[20]), "=r"(w[21]), "=r"(w[22]), "=r"(w[23]), "=r"(w[24]), "=r"(w[25]), "=r"(w[26]), "=r"(w[27]),
+                      "=r"(w[28]), "=r"(w[29]), "=r"(w[30]), "=r"(w[31])
+                    : "r"(ta), "r"(ta + 32u)
+                    : "memory");
+            } else {
+                asm volatile(
+                    "tcgen05.ld.sync.aligned.32x32b.x16.b32 {%0,%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15}, [%16];\n\t"
+                    "tcgen05.wait::ld.sync.aligned;"
+                    : "=r"(w[0]), "=r"(w[1]), "=r"(w[2]), "=r"(w[3]), "=r"(w[4]), "=r"(w[5]), "=r"(w[6]), "=r"(w[7]), "=r"(w[8]), "=r"(w[9]),
+                      "=r"(w[10]), "=r"(w[11]), "=r"(w[12]), "=r"(w[13]), "=r"(w[14]), "=r"(w[15])
+                    : "r"(ta)
+                    : "memory");
             }
+            tc5_fence_before();
+            __syncwarp();
+            if (elect_one()) mbar5_arrive_a(free0 + 8u * ibuf);
+            par ^= ibuf;            // the phase advances when the buffer index wraps (1 -> 0)
+            ibuf ^= 1u;
+            if constexpr (DIAG) {   // a pair with itself: the exact exponent (no cancellation error on the dominant entries of K)
+#pragma unroll
+                for (int gb = 0; gb < (TWO ? 2 : 1); ++gb) {
+                    const int jg = chunk * G + 2 * k + gb;
+                    const float nl = jg < a.J ? __ldg(a.nlc + jg) : D_PAD;
+#pragma unroll
+                    for (int c = 0; c < 16; ++c)
+                        if (c == dcol) w[16 * gb + c] = __float_as_uint(nl);
+                }
+            }
+#pragma unroll
+            for (int c = 0; c < 16; ++c) s[c] += ex2_ftz(-__uint_as_float(w[c]));
+            if constexpr (TWO) {
+#pragma unroll
+                for (int c = 0; c < 16; ++c) s[c] += ex2_ftz(-__uint_as_float(w[16 + c]));
+            }
+            if (tid == 0 || tid == 256) TCD_STAMP(jcur, 5 + (k & 3));
+        };
+        const int nfull = G >> 1;        // batches of two groups; an odd G leaves one batch of one group
+        auto run_batches = [&](auto diag_tag) {
+#pragma unroll 1
+            for (int k = 0; k < nfull; ++k) one_batch(diag_tag, std::true_type{}, k);
+            if (G & 1) one_batch(diag_tag, std::false_type{}, nfull);
         };
 
         int j = 0;                   // j counts the live tiles of BOTH teams
