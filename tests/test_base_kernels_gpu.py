@@ -158,7 +158,12 @@ def test_training_with_an_inverse_multiquadric_kernel_learns_an_additive_target(
     spec["train_kwargs"].update(max_iter=30, check_conv=False)
     torch.manual_seed(3)
     np.random.seed(3)
-    with settings.cg_tolerance(0.01), settings.eval_cg_tolerance(1e-3), warnings.catch_warnings():
+    # eval tolerance 1e-5: the predictive covariance K** - K*^T (K + s^2 I)^-1 K* comes from a CG solve, and with noise 0.08 under
+    # kernel eigenvalues of several hundred a residual of 1e-3 leaves errors of +-0.1 in its spectrum (measured: smallest eigenvalue
+    # -0.016 / -0.093 / -0.218 after 16 / 18 / 17 iterations, tools/debug_imq.py) -- whether the test NLL's Cholesky factor exists is
+    # then a matter of luck (it stopped existing when the lagged convergence check added two iterations).  GPyTorch's
+    # eval_cg_tolerance has the same meaning and the same consequence.
+    with settings.cg_tolerance(0.01), settings.eval_cg_tolerance(1e-5), warnings.catch_warnings():
         warnings.simplefilter("ignore")
         metrics, pred, model = tr.train_exact_gp(X, y, Xt, yt, spec["kind"], spec["model_kwargs"], spec["train_kwargs"],
                                                  devices=("cuda:0",), skip_random_restart=True)
