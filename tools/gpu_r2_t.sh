@@ -1,7 +1,7 @@
 #!/bin/bash
 # round 2, GPU call T/U: lean batch hand-off, loop parameters through volatile shared loads (hard limits on every run)
 mkdir -p gpurun_out
-O=gpurun_out/tcd_x.txt; : > $O
+O=gpurun_out/tcd_y.txt; : > $O
 for shape in "100000 20 5" "100000 1 20" "100000 8 6"; do
   echo "=== base shape=$shape" >> $O
   timeout -s KILL 50 python tools/tcd_check.py time $shape > gpurun_out/q.tmp 2>&1; echo "rc=$?" >> $O; tail -1 gpurun_out/q.tmp >> $O
