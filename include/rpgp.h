@@ -57,11 +57,13 @@ typedef struct {
 } rpgp_layout;
 
 /* base kernels k(d^2) of a projection group (training_routines.py:57-83 `_map_to_kernel`; gp_models/kernels/imq_kernel.py:8-9,47):
- *   RBF exp(-d^2/2);  Matern nu=1.5 (1 + sqrt3 d) exp(-sqrt3 d);  inverse multiquadric (d^2 + 1)^-1/2.
+ *   RBF exp(-d^2/2);  Matern nu=1.5 (1 + sqrt3 d) exp(-sqrt3 d);  inverse multiquadric (d^2 + 1)^-1/2;  cosine cos(d) (gpytorch's
+ *   CosineKernel, training_routines.py:76-81: the caller folds pi / period_length into the coordinates).
  * Every base kernel runs in the SIMT forward / gradient kernels and in the symmetric tensor-core kernel with the same layouts (K = 1:
- * one coordinate and one MUFU per projection -- the distance is |d|, no square root); only the distance-on-tensor-core variant of the
- * symmetric kernel is RBF (its exponent IS the squared distance).  Non-RBF kernels take right-hand-side widths 4 and 16 only. */
-typedef enum { RPGP_BASE_RBF = 0, RPGP_BASE_MATERN15 = 1, RPGP_BASE_INVERSE_MQ = 2 } rpgp_base_kernel;
+ * one coordinate and one MUFU per projection -- the distance is |d|, no square root); the distance-on-tensor-core variant of the
+ * symmetric kernel is RBF only (its exponent IS the squared distance), and the cosine kernel with K > 1 takes the rectangular kernel
+ * (rpgp_mvm_sym_supported says so).  Non-RBF kernels take right-hand-side widths 4 and 16 only. */
+typedef enum { RPGP_BASE_RBF = 0, RPGP_BASE_MATERN15 = 1, RPGP_BASE_INVERSE_MQ = 2, RPGP_BASE_COSINE = 3 } rpgp_base_kernel;
 
 int rpgp_version(void);
 const char* rpgp_last_error(void);

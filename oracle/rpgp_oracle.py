@@ -63,12 +63,16 @@ def scaled_projection(X, W, ell, prescale, dtype=np.float64):
 #   0 RBF  exp(-sq/2)            gpytorch RBFKernel / keops RBFKernel
 #   1 Matern nu=1.5  (1 + sqrt(3 sq)) exp(-sqrt(3 sq))   gpytorch MaternKernel(nu=1.5) [GPyTorch, recalled]
 #   2 inverse multiquadric  (sq + 1)^-1/2   gp_models/kernels/imq_kernel.py:8-9 (postprocess_inverse_mq), :47 (KeOps form)
+#   3 cosine  cos(sqrt(sq))   gpytorch CosineKernel, cos(pi |a - b| / period_length) [GPyTorch, recalled; training_routines.py:76-81,
+#     :150-151]: the kernel class folds pi / period_length into the coordinates
 def base_f(base, sq):
     if base == 1:
         q = np.sqrt(3.0 * sq)
         return (1.0 + q) * np.exp(-q)
     if base == 2:
         return 1.0 / np.sqrt(sq + 1.0)
+    if base == 3:
+        return np.cos(np.sqrt(sq))
     return np.exp(-0.5 * sq)
 
 
@@ -78,6 +82,11 @@ def base_df(base, sq):
         return -1.5 * np.exp(-np.sqrt(3.0 * sq))
     if base == 2:
         return -0.5 * (sq + 1.0) ** -1.5
+    if base == 3:        # -sin(d) / (2 d), -> -1/2 at the origin
+        d = np.sqrt(sq)
+        with np.errstate(divide="ignore", invalid="ignore"):
+            q = -0.5 * np.sin(d) / d
+        return np.where(d < 1e-6, -0.5 + sq / 12.0, q)
     return -0.5 * np.exp(-0.5 * sq)
 
 

@@ -47,7 +47,7 @@ static int check_layout(const rpgp_layout* lay) {
     RPGP_REQUIRE(lay->nchunks >= 1 && lay->G >= 1 && lay->KP >= 1, "layout: nchunks/G/KP must be >= 1");
     RPGP_REQUIRE(lay->KP >= lay->K && lay->G * lay->KP <= lay->CP, "layout: group shape KP=%d G=%d exceeds CP=%d", lay->KP, lay->G, lay->CP);
     RPGP_REQUIRE((long long)lay->nchunks * lay->G >= lay->J, "layout: %d chunks x %d groups < J=%d", lay->nchunks, lay->G, lay->J);
-    RPGP_REQUIRE(lay->base >= 0 && lay->base <= 2, "layout: base kernel %d (0 RBF, 1 Matern-1.5, 2 inverse multiquadric)", lay->base);
+    RPGP_REQUIRE(lay->base >= 0 && lay->base <= 3, "layout: base kernel %d (0 RBF, 1 Matern-1.5, 2 inverse multiquadric, 3 cosine)", lay->base);
     RPGP_REQUIRE((lay->K == 1) == (lay->KP == 1), "layout: KP must be 1 exactly when K is 1");
     RPGP_REQUIRE(lay->KP > 1 || lay->G == lay->CP, "layout: K=1 requires G == CP");
     return OK;
@@ -85,7 +85,7 @@ int rpgp_plan_layout(int J, int K, rpgp_layout* out) { return rpgp_plan_layout_b
 int rpgp_plan_layout_base(int J, int K, int base, rpgp_layout* out) {
     RPGP_REQUIRE(out != nullptr, "plan_layout: out is NULL");
     RPGP_REQUIRE(J >= 1 && K >= 1, "plan_layout: J=%d K=%d must be >= 1", J, K);
-    RPGP_REQUIRE(base >= 0 && base <= 2, "plan_layout: base kernel %d (0 RBF, 1 Matern-1.5, 2 inverse multiquadric)", base);
+    RPGP_REQUIRE(base >= 0 && base <= 3, "plan_layout: base kernel %d (0 RBF, 1 Matern-1.5, 2 inverse multiquadric, 3 cosine)", base);
     out->J = J;
     out->K = K;
     out->base = base;
@@ -242,7 +242,9 @@ int rpgp_mvm_sym_distance_plan(const rpgp_layout* lay, int plan[5]) {
 }
 
 int rpgp_mvm_sym_supported(const rpgp_layout* lay, int t) {
-    return lay && check_layout(lay) == OK && t >= 1 && t <= 16;     // every base kernel (the distance-on-tensor-core variant is RBF only)
+    // every base kernel for K = 1; K > 1: RBF, Matern-1.5, inverse MQ (the cosine kernel with K > 1 stays on the rectangular kernel; the
+    // distance-on-tensor-core variant is RBF only)
+    return lay && check_layout(lay) == OK && t >= 1 && t <= 16 && !(lay->base == 3 && lay->KP > 1);
 }
 
 int rpgp_mvm_sym_f32(const float* zp, int64_t n, const rpgp_layout* lay, const float* neg_log2c, const float* Vp16, int t,
@@ -317,14 +319,14 @@ int rpgp_quad_bwd_f32(const float* z1p, int64_t m, int64_t z1_stride, const floa
 int rpgp_kernel_rows_base_f32(const float* Zr, int64_t P, const float* Z2, int64_t n, int64_t ld, int J, int K, int base,
                               const float* c, float* out, int64_t ldo, void* stream) {
     RPGP_REQUIRE(P >= 0 && n >= 0 && J >= 1 && K >= 1 && ld >= (int64_t)J * K && ldo >= n, "kernel_rows: bad shape");
-    RPGP_REQUIRE(base >= 0 && base <= 2, "kernel_rows: base kernel %d", base);
+    RPGP_REQUIRE(base >= 0 && base <= 3, "kernel_rows: base kernel %d", base);
     RPGP_REQUIRE((P == 0 || n == 0) || (Zr && Z2 && c && out), "kernel_rows: NULL pointer");
     return launch_rows_f32(Zr, P, Z2, n, ld, J, K, base, c, out, ldo, (cudaStream_t)stream);
 }
 int rpgp_kernel_rows_base_f64(const double* Zr, int64_t P, const double* Z2, int64_t n, int64_t ld, int J, int K, int base,
                               const double* c, double* out, int64_t ldo, void* stream) {
     RPGP_REQUIRE(P >= 0 && n >= 0 && J >= 1 && K >= 1 && ld >= (int64_t)J * K && ldo >= n, "kernel_rows: bad shape");
-    RPGP_REQUIRE(base >= 0 && base <= 2, "kernel_rows: base kernel %d", base);
+    RPGP_REQUIRE(base >= 0 && base <= 3, "kernel_rows: base kernel %d", base);
     RPGP_REQUIRE((P == 0 || n == 0) || (Zr && Z2 && c && out), "kernel_rows: NULL pointer");
     return launch_rows_f64(Zr, P, Z2, n, ld, J, K, base, c, out, ldo, (cudaStream_t)stream);
 }
@@ -340,14 +342,14 @@ int rpgp_kernel_rows_f64(const double* Zr, int64_t P, const double* Z2, int64_t 
 int rpgp_mvm_fwd_base_f64(const double* Z1, int64_t m, const double* Z2, int64_t n, int64_t ld, int J, int K, int base,
                           const double* c, const double* V, int t, double* out, void* stream) {
     RPGP_REQUIRE(m >= 0 && n >= 0 && J >= 1 && K >= 1 && t >= 1 && ld >= (int64_t)J * K, "mvm_fwd_f64: bad shape");
-    RPGP_REQUIRE(base >= 0 && base <= 2, "mvm_fwd_f64: base kernel %d", base);
+    RPGP_REQUIRE(base >= 0 && base <= 3, "mvm_fwd_f64: base kernel %d", base);
     RPGP_REQUIRE(m == 0 || (Z1 && c && out && (n == 0 || (Z2 && V))), "mvm_fwd_f64: NULL pointer");
     return launch_mvm_f64(Z1, m, Z2, n, ld, J, K, base, c, V, t, out, (cudaStream_t)stream);
 }
 int rpgp_quad_bwd_base_f64(const double* Z1, int64_t m, const double* Z2, int64_t n, int64_t ld, int J, int K, int base,
                            const double* c, const double* L, const double* R, int t, double* dZ1, double* g, void* stream) {
     RPGP_REQUIRE(m >= 0 && n >= 0 && J >= 1 && K >= 1 && t >= 1 && ld >= (int64_t)J * K, "quad_bwd_f64: bad shape");
-    RPGP_REQUIRE(base >= 0 && base <= 2, "quad_bwd_f64: base kernel %d", base);
+    RPGP_REQUIRE(base >= 0 && base <= 3, "quad_bwd_f64: base kernel %d", base);
     RPGP_REQUIRE(m == 0 || n == 0 || (Z1 && Z2 && c && L && R && dZ1 && g), "quad_bwd_f64: NULL pointer");
     if (n == 0) return OK;
     return launch_quad_f64(Z1, m, Z2, n, ld, J, K, base, c, L, R, t, dZ1, g, (cudaStream_t)stream);

@@ -85,6 +85,7 @@ __device__ __forceinline__ T base_f(int base, T sq) {
         return (T(1) + q) * exp(-q);
     }
     if (base == 2) return T(1) / sqrt(sq + T(1));
+    if (base == 3) return cos(sqrt(sq));
     return exp(T(-0.5) * sq);
 }
 template <typename T>
@@ -93,6 +94,10 @@ __device__ __forceinline__ T base_df(int base, T sq) {
     if (base == 2) {
         const T r = T(1) / sqrt(sq + T(1));
         return T(-0.5) * r * r * r;
+    }
+    if (base == 3) {        // d cos(sqrt(sq)) / dsq = -sin(d) / (2 d)
+        const T d = sqrt(sq);
+        return d < T(1e-4) ? T(-0.5) + sq / T(12) : T(-0.5) * sin(d) / d;
     }
     return T(-0.5) * exp(T(-0.5) * sq);
 }

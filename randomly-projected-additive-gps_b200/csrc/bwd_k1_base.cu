@@ -1,4 +1,4 @@
-// bwd_k1_base.cu -- the quadratic-form row-gradient kernel for K = 1 with the Matern-1.5 and inverse-multiquadric base kernels
+// bwd_k1_base.cu -- the quadratic-form row-gradient kernel for K = 1 with the Matern-1.5, inverse-multiquadric and cosine base kernels
 // (kv_kernels.cuh base_value_slope_k1), right-hand-side widths 4 and 16.
 #include "dispatch.cuh"
 namespace rpgp {
@@ -7,6 +7,7 @@ int launch_grad_k1_base(int CP, int TP, int base, const GradArgs& a, dim3 grid, 
     if (CP == CPv && TP == TPv) {                                                                         \
         if (base == BASE_MATERN15) return run_grad<CPv, TPv, 1, CPv, BASE_MATERN15>(a, grid, st);         \
         if (base == BASE_IMQ) return run_grad<CPv, TPv, 1, CPv, BASE_IMQ>(a, grid, st);                   \
+        if (base == BASE_COS) return run_grad<CPv, TPv, 1, CPv, BASE_COS>(a, grid, st);                   \
     }
     RPGP_K1_CP_LIST(RPGP_CASE, 4)
     RPGP_K1_CP_LIST(RPGP_CASE, 16)

@@ -1,4 +1,4 @@
-// bwd_kn_base.cu -- the quadratic-form row-gradient kernel with the Matern-1.5 and inverse-multiquadric base kernels
+// bwd_kn_base.cu -- the quadratic-form row-gradient kernel with the Matern-1.5, inverse-multiquadric and cosine base kernels
 // (kv_kernels.cuh base_value_slope).
 #include "dispatch.cuh"
 namespace rpgp {
@@ -7,6 +7,7 @@ int launch_grad_kn_base(int KP, int G, int CP, int TP, int base, const GradArgs&
     if (KP == KPv && G == Gv && CP == CPv && TP == TPv) {                                                 \
         if (base == BASE_MATERN15) return run_grad<CPv, TPv, KPv, Gv, BASE_MATERN15>(a, grid, st);        \
         if (base == BASE_IMQ) return run_grad<CPv, TPv, KPv, Gv, BASE_IMQ>(a, grid, st);                  \
+        if (base == BASE_COS) return run_grad<CPv, TPv, KPv, Gv, BASE_COS>(a, grid, st);                  \
     }
     RPGP_KN_SHAPE_LIST(RPGP_CASE, 4)
     RPGP_KN_SHAPE_LIST(RPGP_CASE, 16)

@@ -1,4 +1,4 @@
-// fwd_k1_base.cu -- the forward K.V kernel for K = 1 with the Matern-1.5 and inverse-multiquadric base kernels: the native K = 1 layout
+// fwd_k1_base.cu -- the forward K.V kernel for K = 1 with the Matern-1.5, inverse-multiquadric and cosine base kernels: the native K = 1 layout
 // (one coordinate per projection, one MUFU per projection: kv_kernels.cuh base_value_k1), right-hand-side widths 4 and 16.
 #include "dispatch.cuh"
 namespace rpgp {
@@ -7,6 +7,7 @@ int launch_fwd_k1_base(int CP, int TP, int base, const MvmArgs& a, dim3 grid, cu
     if (CP == CPv && TP == TPv) {                                                                            \
         if (base == BASE_MATERN15) return run_fwd<CPv, TPv, 1, CPv, 0, BASE_MATERN15>(a, grid, st);          \
         if (base == BASE_IMQ) return run_fwd<CPv, TPv, 1, CPv, 0, BASE_IMQ>(a, grid, st);                    \
+        if (base == BASE_COS) return run_fwd<CPv, TPv, 1, CPv, 0, BASE_COS>(a, grid, st);                    \
     }
     RPGP_K1_CP_LIST(RPGP_CASE, 4)
     RPGP_K1_CP_LIST(RPGP_CASE, 16)

@@ -1,4 +1,4 @@
-// fwd_kn_base.cu -- the forward K.V kernel with the Matern-1.5 and inverse-multiquadric base kernels: the same
+// fwd_kn_base.cu -- the forward K.V kernel with the Matern-1.5, inverse-multiquadric and cosine base kernels: the same
 // tile structure as the RBF kernel, a different function of the group's squared distance (kv_kernels.cuh base_value).
 #include "dispatch.cuh"
 namespace rpgp {
@@ -7,6 +7,7 @@ int launch_fwd_kn_base(int KP, int G, int CP, int TP, int base, const MvmArgs& a
     if (KP == KPv && G == Gv && CP == CPv && TP == TPv) {                                                    \
         if (base == BASE_MATERN15) return run_fwd<CPv, TPv, KPv, Gv, 0, BASE_MATERN15>(a, grid, st);         \
         if (base == BASE_IMQ) return run_fwd<CPv, TPv, KPv, Gv, 0, BASE_IMQ>(a, grid, st);                   \
+        if (base == BASE_COS) return run_fwd<CPv, TPv, KPv, Gv, 0, BASE_COS>(a, grid, st);                   \
     }
     RPGP_KN_SHAPE_LIST(RPGP_CASE, 4)
     RPGP_KN_SHAPE_LIST(RPGP_CASE, 16)

@@ -77,7 +77,7 @@ struct RowCoords {
 // ---- base kernels (training_routines.py:57-83, imq_kernel.py:8-9,47) ---------------------------------------------
 // u = scaled squared distance of a group (natural d^2 = 2 ln2 * u).  value: k = c f(d^2); slope: kz = -(dk/du) / ln2, the factor the
 // row-gradient kernel multiplies the coordinate differences with (its reducer applies -2 ln2, which is exact for the RBF k = 2^-u).
-constexpr int BASE_RBF = 0, BASE_MATERN15 = 1, BASE_IMQ = 2;
+constexpr int BASE_RBF = 0, BASE_MATERN15 = 1, BASE_IMQ = 2, BASE_COS = 3;
 constexpr float MATERN_C = 4.1588830833596715f;      // 3 * 2 ln2: (sqrt3 r)^2 = MATERN_C * u
 constexpr float TWO_LN2_F = 1.3862943611198906f;
 
@@ -93,6 +93,33 @@ __device__ __forceinline__ float rsqrt_approx_ftz(float x) {
     return y;
 }
 
+// cosine base kernel (gpytorch.kernels.CosineKernel as training_routines.py:76-81 selects it): k = c cos(d), d the natural distance of
+// the group -- the kernel classes fold pi / period_length into the coordinates.  cos.approx / sin.approx are accurate to 2^-20.9 only
+// near the origin, so the argument is first reduced to [-pi, pi] with a two-term Cody-Waite split of 2 pi (exact for |d| < 2^18).
+__device__ __forceinline__ float reduce_2pi(float d) {
+    // n = round(d / 2 pi) by the 1.5 * 2^23 magic constant: rintf is an FRND on the quarter-rate conversion pipe, which this kernel's
+    // one MUFU per projection already fills (first version: 49 ms at the cfg2 shape against 26 ms for the other base kernels)
+    const float n = __fadd_rn(fmaf(d, 0.15915494309189535f, 12582912.f), -12582912.f);
+    float r = fmaf(n, -6.2831854820251465f, d);      // 2 pi rounded to FP32 ...
+    return fmaf(n, 1.7484555314695172e-07f, r);     // ... and the remainder (2 pi = 6.2831854820251465 - 1.7484555e-7)
+}
+__device__ __forceinline__ float cos_approx_ftz(float x) {
+    float y;
+    asm("cos.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
+    return y;
+}
+__device__ __forceinline__ float sin_approx_ftz(float x) {
+    float y;
+    asm("sin.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
+    return y;
+}
+// sin(d) / d for the gradient (1 - d^2 / 6 near the origin, where the quotient loses its digits)
+__device__ __forceinline__ float sinc_of(float d) {
+    const float q = sin_approx_ftz(reduce_2pi(d)) * __frcp_rn(fmaxf(d, 1e-20f));
+    return d < 0.02f ? fmaf(d * d, -0.16666667f, 1.f) : q;
+}
+constexpr float INV_SCALE_F = 1.1774100225154747f;   // natural coordinate = packed coordinate * sqrt(2 ln 2)
+
 template <int BASE>
 __device__ __forceinline__ float base_value(float u, float nl, float cw) {
     if constexpr (BASE == BASE_RBF) {
@@ -101,8 +128,10 @@ __device__ __forceinline__ float base_value(float u, float nl, float cw) {
         const float q = sqrt_approx_ftz(fmaxf(MATERN_C * u, 0.f));
         const float e = ex2_ftz(-q * LOG2E_F);
         return cw * fmaf(q, e, e);
-    } else {
+    } else if constexpr (BASE == BASE_IMQ) {
         return cw * rsqrt_approx_ftz(fmaf(TWO_LN2_F, u, 1.f));
+    } else {
+        return cw * cos_approx_ftz(reduce_2pi(sqrt_approx_ftz(fmaxf(TWO_LN2_F * u, 0.f))));
     }
 }
 
@@ -116,10 +145,14 @@ __device__ __forceinline__ void base_value_slope(float u, float nl, float cw, fl
         const float e = cw * ex2_ftz(-q * LOG2E_F);
         k = fmaf(q, e, e);
         kz = 3.f * e;                      // -dk/du = c (MATERN_C / 2) e^-q ; / ln2 = 3 c e^-q
-    } else {
+    } else if constexpr (BASE == BASE_IMQ) {
         const float rs = rsqrt_approx_ftz(fmaf(TWO_LN2_F, u, 1.f));
         k = cw * rs;
         kz = k * rs * rs;                  // -dk/du = c ln2 rs^3
+    } else {
+        const float d = sqrt_approx_ftz(fmaxf(TWO_LN2_F * u, 0.f));
+        k = cw * cos_approx_ftz(reduce_2pi(d));
+        kz = cw * sinc_of(d);              // -dk/du = c sin(d) (2 ln2) / (2 d); / ln2 = c sin(d) / d
     }
 }
 
@@ -127,6 +160,7 @@ __device__ __forceinline__ void base_value_slope(float u, float nl, float cw, fl
 // no square root is needed -- the distance is |d| -- so every base kernel costs ONE MUFU per projection, like the RBF.
 //   Matern-1.5: q = sqrt3 |d_nat| = |ds| sqrt(MATERN_C);  a = q log2(e);  k = c 2^-a (1 + a ln2);  kz = -(dk/du)/ln2 = 3 c 2^-a
 //   inverse MQ: k = c rsqrt(1 + 2 ln2 ds^2);  kz = k rs^2
+//   cosine:     k = c cos(|d_nat|);  kz = c sin(|d_nat|) / |d_nat|   (two MUFU in the gradient: sin and the reciprocal)
 constexpr float MATERN_A = 2.942137020149432f;  // sqrt(MATERN_C) * log2(e)
 constexpr float LN2_F = 0.6931471805599453f;
 template <int BASE>
@@ -138,11 +172,13 @@ __device__ __forceinline__ f32x2 base_value_k1(f32x2 d, f32x2 cw) {
         const f32x2 e = pack2(ex2_ftz(-al), ex2_ftz(-ah));
         const f32x2 u = fma2(pack2(al, ah), pack2(LN2_F, LN2_F), pack2(1.f, 1.f));
         return mul2(mul2(cw, e), u);
-    } else {
+    } else if constexpr (BASE == BASE_IMQ) {
         const f32x2 t = fma2(d, mul2(d, pack2(TWO_LN2_F, TWO_LN2_F)), pack2(1.f, 1.f));
         float tl, th;
         unpack2(t, tl, th);
         return mul2(cw, pack2(rsqrt_approx_ftz(tl), rsqrt_approx_ftz(th)));
+    } else {        // cosine: even in d, no absolute value needed
+        return mul2(cw, pack2(cos_approx_ftz(reduce_2pi(dl * INV_SCALE_F)), cos_approx_ftz(reduce_2pi(dh * INV_SCALE_F))));
     }
 }
 template <int BASE>
@@ -154,13 +190,17 @@ __device__ __forceinline__ void base_value_slope_k1(f32x2 d, f32x2 cw, f32x2& k,
         const f32x2 e = mul2(cw, pack2(ex2_ftz(-al), ex2_ftz(-ah)));
         k = mul2(e, fma2(pack2(al, ah), pack2(LN2_F, LN2_F), pack2(1.f, 1.f)));
         kz = mul2(e, pack2(3.f, 3.f));
-    } else {
+    } else if constexpr (BASE == BASE_IMQ) {
         const f32x2 t = fma2(d, mul2(d, pack2(TWO_LN2_F, TWO_LN2_F)), pack2(1.f, 1.f));
         float tl, th;
         unpack2(t, tl, th);
         const f32x2 rs = pack2(rsqrt_approx_ftz(tl), rsqrt_approx_ftz(th));
         k = mul2(cw, rs);
         kz = mul2(k, mul2(rs, rs));
+    } else {
+        const float al = fabsf(dl) * INV_SCALE_F, ah = fabsf(dh) * INV_SCALE_F;
+        k = mul2(cw, pack2(cos_approx_ftz(reduce_2pi(al)), cos_approx_ftz(reduce_2pi(ah))));
+        kz = mul2(cw, pack2(sinc_of(al), sinc_of(ah)));
     }
 }
 

@@ -428,15 +428,17 @@ int launch_sym_tc5(const float* zp, long long n, const Layout& lay, const float*
         dim3 grid((unsigned)nrb, (unsigned)a.nsplits, (unsigned)lay.nchunks);
         int rc = ERR_UNSUPPORTED;
         if (KP == 1 && lay.base != 0) {
-            // K = 1 with the Matern-1.5 / inverse-multiquadric base kernel: one MUFU per projection (no square root: the distance is |d|)
+            // K = 1 with the Matern-1.5 / inverse-multiquadric / cosine base kernel: one MUFU per projection (no square root: the distance is |d|)
 #define RPGP_SYM5_K1B(CPv)                                                                                             \
             if (CP == CPv) {                                                                                           \
                 if constexpr (CPv <= 24)                                                                               \
                     rc = lay.base == BASE_MATERN15 ? run_sym5<CPv, 1, CPv, 0, 2, BASE_MATERN15>(a, grid, st)           \
-                                                   : run_sym5<CPv, 1, CPv, 0, 2, BASE_IMQ>(a, grid, st);               \
+                         : lay.base == BASE_IMQ    ? run_sym5<CPv, 1, CPv, 0, 2, BASE_IMQ>(a, grid, st)                \
+                                                   : run_sym5<CPv, 1, CPv, 0, 2, BASE_COS>(a, grid, st);               \
                 else                                                                                                   \
                     rc = lay.base == BASE_MATERN15 ? run_sym5<CPv, 1, CPv, 0, 1, BASE_MATERN15>(a, grid, st)           \
-                                                   : run_sym5<CPv, 1, CPv, 0, 1, BASE_IMQ>(a, grid, st);               \
+                         : lay.base == BASE_IMQ    ? run_sym5<CPv, 1, CPv, 0, 1, BASE_IMQ>(a, grid, st)                \
+                                                   : run_sym5<CPv, 1, CPv, 0, 1, BASE_COS>(a, grid, st);               \
             }
             RPGP_SYM5_K1B(4) RPGP_SYM5_K1B(8) RPGP_SYM5_K1B(12) RPGP_SYM5_K1B(16) RPGP_SYM5_K1B(20) RPGP_SYM5_K1B(24) RPGP_SYM5_K1B(28) RPGP_SYM5_K1B(32)
 #undef RPGP_SYM5_K1B

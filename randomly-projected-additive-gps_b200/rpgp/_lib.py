@@ -133,7 +133,7 @@ def _stream(device=None):
 _layout_cache = {}
 
 
-BASE_RBF, BASE_MATERN15, BASE_INVERSE_MQ = 0, 1, 2      # rpgp_base_kernel (include/rpgp.h)
+BASE_RBF, BASE_MATERN15, BASE_INVERSE_MQ, BASE_COSINE = 0, 1, 2, 3      # rpgp_base_kernel (include/rpgp.h)
 
 
 def plan_layout(J, K, base=BASE_RBF):

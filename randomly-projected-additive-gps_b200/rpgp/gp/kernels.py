@@ -8,6 +8,8 @@ collapses into ONE fused operator whose products run in the sm_100a kernels.  Pa
 (`kernel.kernels.0.base_kernel.kernels.1.raw_lengthscale`, `raw_outputscale`, ...) match GPyTorch's so state-dicts and
 the reference's tests/utilities keep working (test.py:126-134, utils.py:12-29).
 """
+import math
+
 import torch
 
 from ..lazy import LazyTensor, RPAdditiveLazyTensor
@@ -193,6 +195,40 @@ class InverseMQKernel(MaternKernel):
 
     def __init__(self, **kwargs):
         RBFKernel.__init__(self, **kwargs)
+
+
+class CosineKernel(Kernel):
+    """cos(pi |a - b| / period_length) (gpytorch.kernels.CosineKernel, which the reference's `_map_to_kernel` selects for
+    kernel_type 'Cosine', training_routines.py:76-81; no lengthscale: `create_additive_rp_kernel` initialises period_length instead,
+    :150-151).  Lowers to base kernel 3 of the fused kernels with pi / period_length folded into the coordinates."""
+    has_lengthscale = False
+    _base = 3
+
+    def __init__(self, period_length_prior=None, period_length_constraint=None, **kwargs):
+        super().__init__(**kwargs)
+        self.register_parameter("raw_period_length", torch.nn.Parameter(torch.zeros(1, 1)))
+        self.register_constraint("raw_period_length", period_length_constraint or Positive())
+        if period_length_prior is not None:
+            self.register_prior("period_length_prior", period_length_prior, lambda m: m.period_length)
+
+    @property
+    def period_length(self):
+        return self.raw_period_length_constraint.transform(self.raw_period_length)
+
+    @period_length.setter
+    def period_length(self, value):
+        self._set_constrained("raw_period_length", value)
+
+    def forward(self, x1, x2, diag=False, last_dim_is_batch=False, **params):
+        same = _same_points(x1, x2)
+        scale = math.pi / self.period_length
+        z1 = x1 * scale
+        z2 = None if same else x2 * scale
+        D = x1.shape[-1]
+        one = torch.ones(1, dtype=x1.dtype, device=x1.device)
+        op = RPAdditiveLazyTensor(z1, z2, one.expand(D), D, 1) if last_dim_is_batch else RPAdditiveLazyTensor(z1, z2, one, 1, D)
+        op.base = self._base
+        return op
 
 
 class ScaleKernel(Kernel):

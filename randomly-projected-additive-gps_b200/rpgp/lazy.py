@@ -79,6 +79,8 @@ def base_function(base, sq):
         return (1.0 + q) * torch.exp(-q)
     if base == 2:
         return (sq + 1.0).rsqrt()
+    if base == 3:
+        return torch.cos(sq.clamp_min(0).sqrt())
     return torch.exp(-0.5 * sq)
 
 

@@ -25,7 +25,7 @@ from gp_models.kernels import (CustomAdditiveKernel, GeneralizedProjectionKernel
                                PolynomialProjectionKernel, ScaledProjectionKernel, StrictlyAdditiveKernel)
 from gp_models.models import ExactGPModel
 from rpgp import gp as gpytorch
-from rpgp.gp.kernels import InverseMQKernel, MaternKernel, RBFKernel, ScaleKernel
+from rpgp.gp.kernels import CosineKernel, InverseMQKernel, MaternKernel, RBFKernel, ScaleKernel
 
 SPEC_DIR = os.path.join(os.path.dirname(os.path.abspath(__file__)), "model_specs")
 HOT_PATH_KINDS = ("rp_poly", "additive_rp", "strictly_additive", "additive", "general_rp_poly")
@@ -67,9 +67,8 @@ def _sample_from_range(num_samples, range_):
 
 def _map_to_kernel(return_object, kernel_type, keops, **key_words):
     """Base-kernel lookup (reference :52-83).  `keops` is accepted and ignored: there is a single backend -- the hand-written
-    kernels replace both the dense and the KeOps route of the reference.  RBF, Matern (nu = 1.5) and the inverse multiquadric run
-    in the fused kernels; the cosine kernel is not a function of the squared distance the operator is built on (and has no KeOps
-    form in the reference either)."""
+    kernels replace both the dense and the KeOps route of the reference.  RBF, Matern (nu = 1.5), the inverse multiquadric and the
+    cosine kernel (dense-only in the reference, :76-81) are base kernels 0..3 of the fused kernels."""
     if return_object:
         cls, kwargs = _map_to_kernel(False, kernel_type, keops)
         return cls(**key_words, **kwargs)
@@ -80,7 +79,7 @@ def _map_to_kernel(return_object, kernel_type, keops, **key_words):
     if kernel_type == "InverseMQ":
         return InverseMQKernel, dict(**key_words)
     if kernel_type == "Cosine":
-        raise NotImplementedError("the cosine base kernel is outside the fused K.V path (DESIGN.md §9)")
+        return CosineKernel, dict(**key_words)
     raise ValueError("Unknown kernel type")
 
 
@@ -122,7 +121,10 @@ def create_additive_rp_kernel(d, J, learn_proj=False, kernel_type="RBF", space_p
 
     def make_kernel(active_dim=None):
         kernel = _map_to_kernel(True, kernel_type, keops, active_dims=active_dim)
-        kernel.initialize(lengthscale=torch.tensor([1.]))
+        if hasattr(kernel, "period_length"):      # the cosine kernel has no lengthscale (reference :150-153)
+            kernel.initialize(period_length=torch.tensor([1.]))
+        else:
+            kernel.initialize(lengthscale=torch.tensor([1.]))
         kernel = ScaleKernel(kernel)
         kernel.initialize(outputscale=torch.tensor([1 / J]))
         return kernel

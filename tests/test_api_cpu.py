@@ -261,6 +261,9 @@ def test_distance_on_tensor_core_plan_and_base_layouts():
     assert _lib.padded_rhs(mat, 11, False) == 16 and _lib.padded_rhs(rbf, 11, False) == 12
     imq = _lib.plan_layout(3, 4, _lib.BASE_INVERSE_MQ)
     assert imq.base == 2 and imq.KP >= 4
+    cos1, cos4 = _lib.plan_layout(20, 1, _lib.BASE_COSINE), _lib.plan_layout(3, 4, _lib.BASE_COSINE)
+    assert cos1.base == 3 and (cos1.KP, cos1.CP) == (1, 20) and _lib.mvm_sym_supported(cos1, 11)
+    assert not _lib.mvm_sym_supported(cos4, 11)       # the cosine kernel with K > 1 takes the rectangular kernel
     with pytest.raises(RuntimeError):
         _lib.plan_layout(3, 4, 7)
 

@@ -11,22 +11,23 @@ from rpgp import lazy
 from rpgp.gp import kernels as gk
 
 
-@pytest.mark.parametrize("base", [0, 1, 2])
+@pytest.mark.parametrize("base", [0, 1, 2, 3])
 def test_oracle_base_functions_and_slopes(base):
     sq = np.linspace(0.0, 30.0, 301)[1:]
     h = 1e-6
     fd = (orc.base_f(base, sq + h) - orc.base_f(base, sq - h)) / (2 * h)
     np.testing.assert_allclose(orc.base_df(base, sq), fd, rtol=1e-6, atol=1e-10)
-    assert abs(orc.base_f(base, np.array([0.0]))[0] - 1.0) < 1e-15            # k(x, x) = 1 for all three
+    assert abs(orc.base_f(base, np.array([0.0]))[0] - 1.0) < 1e-15            # k(x, x) = 1 for all four
+    assert abs(orc.base_df(base, np.array([0.0]))[0] - (-1.5 if base == 1 else -0.5)) < 1e-12      # finite slope at the origin
     t = torch.from_numpy(sq)
     np.testing.assert_allclose(lazy.base_function(base, t).numpy(), orc.base_f(base, sq), rtol=1e-12)
 
 
 def test_oracle_dense_kernel_known_values():
-    # one group, one coordinate, distance 2: RBF e^-2, Matern (1 + 2 sqrt3) e^(-2 sqrt3), IMQ 5^-1/2
+    # one group, one coordinate, distance 2: RBF e^-2, Matern (1 + 2 sqrt3) e^(-2 sqrt3), IMQ 5^-1/2, cosine cos 2
     Z1, Z2 = np.array([[0.0]]), np.array([[2.0]])
-    want = [np.exp(-2.0), (1 + 2 * np.sqrt(3)) * np.exp(-2 * np.sqrt(3)), 5 ** -0.5]
-    for base in range(3):
+    want = [np.exp(-2.0), (1 + 2 * np.sqrt(3)) * np.exp(-2 * np.sqrt(3)), 5 ** -0.5, np.cos(2.0)]
+    for base in range(4):
         assert abs(orc.additive_rbf_dense(Z1, Z2, [1.0], 1, 1, base=base)[0, 0] - want[base]) < 1e-15
     assert abs(float(postprocess_inverse_mq(torch.tensor(4.0))) - want[2]) < 1e-7      # imq_kernel.py:8-9
 
@@ -37,8 +38,7 @@ def test_kernel_type_lookup_matches_the_reference_table():
     assert tr._map_to_kernel(False, "InverseMQ", False) == (gk.InverseMQKernel, {})
     assert MirrorIMQ is gk.InverseMQKernel and KeOpsInverseMQKernel is gk.InverseMQKernel
     assert gk.keops.RBFKernel is gk.RBFKernel and gk.keops.MaternKernel is gk.MaternKernel
-    with pytest.raises(NotImplementedError):
-        tr._map_to_kernel(False, "Cosine", False)
+    assert tr._map_to_kernel(False, "Cosine", False) == (gk.CosineKernel, {})       # (dense-only in the reference, :76-81)
     with pytest.raises(ValueError):
         tr._map_to_kernel(False, "Periodic", False)
     k = tr._map_to_kernel(True, "Matern", False, active_dims=[0])
@@ -62,7 +62,34 @@ def test_operators_of_different_base_kernels_do_not_merge():
     assert op.base == 2
 
 
-@pytest.mark.parametrize("base", [0, 1, 2])
+def test_cosine_kernel_is_gpytorchs_cosine_kernel():
+    """gpytorch.kernels.CosineKernel: cos(pi |a - b| / period_length), one positive `raw_period_length` of shape (1, 1), no
+    lengthscale; the reference's additive factory initialises period_length = 1 where the others get lengthscale = 1
+    (training_routines.py:150-153).  The class lowers to base kernel 3 with pi / p folded into the coordinates."""
+    k = gk.CosineKernel()
+    assert tuple(k.raw_period_length.shape) == (1, 1) and k.lengthscale is None and not k.has_lengthscale
+    with pytest.raises(RuntimeError):
+        k.lengthscale = 1.0
+    k.initialize(period_length=torch.tensor([2.5]))
+    np.testing.assert_allclose(float(k.period_length), 2.5, rtol=1e-6)
+    g = torch.Generator().manual_seed(0)
+    x1, x2 = torch.randn(7, 3, generator=g, dtype=torch.float64), torch.randn(5, 3, generator=g, dtype=torch.float64)
+    k = k.double()
+    k.initialize(period_length=torch.tensor([2.5], dtype=torch.float64))
+    op = k.forward(x1, x2)
+    assert op.base == 3 and (op.J, op.K) == (1, 3)
+    dense = orc.additive_rbf_dense(op.Z1.detach().numpy(), op.Z2.detach().numpy(), [1.0], 1, 3, base=3)
+    want = np.cos(np.pi * torch.cdist(x1, x2).numpy() / 2.5)
+    np.testing.assert_allclose(dense, want, rtol=1e-10, atol=1e-12)
+    per_dim = k.forward(x1, x1, last_dim_is_batch=True)           # AdditiveStructureKernel's way: one 1-D kernel per input dimension
+    assert per_dim.base == 3 and (per_dim.J, per_dim.K) == (3, 1) and per_dim.Z2 is None
+    kern = tr.create_additive_rp_kernel(4, 3, kernel_type="Cosine", batch_kernel=False, mem_efficient=False)
+    subs = kern.base_kernel.kernels
+    assert all(isinstance(s.base_kernel, gk.CosineKernel) and abs(float(s.base_kernel.period_length) - 1.0) < 1e-6 for s in subs)
+    assert all(abs(float(s.outputscale) - 1 / 3) < 1e-6 for s in subs)
+
+
+@pytest.mark.parametrize("base", [0, 1, 2, 3])
 def test_operator_diagonals_need_no_kernel_launch(base):
     """diag of K(Z, Z) is sum_j c_j for every base kernel (k(0) = 1); diag of a square K(Z1, Z2) is formed in torch"""
     g = torch.Generator().manual_seed(base)

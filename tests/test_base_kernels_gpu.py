@@ -1,4 +1,4 @@
-"""GPU parity of the Matern-1.5 and inverse-multiquadric base kernels (reference training_routines.py:57-83,
+"""GPU parity of the Matern-1.5, inverse-multiquadric and cosine base kernels (reference training_routines.py:57-83,
 gp_models/kernels/imq_kernel.py) through the fused forward / gradient kernels, the dense-row kernel and the FP64 path, against
 the numpy oracle; then through the reference-facing kernel classes."""
 import warnings
@@ -30,7 +30,7 @@ def data(m, n, J, K, t, seed):
     return Z1, Z2, c, V
 
 
-@pytest.mark.parametrize("base", [1, 2])
+@pytest.mark.parametrize("base", [1, 2, 3])
 @pytest.mark.parametrize("m,n,J,K,t", [(300, 700, 20, 1, 11), (257, 513, 7, 3, 4), (400, 400, 1, 20, 16), (130, 900, 40, 1, 1),
                                        (64, 2000, 20, 5, 11)])
 def test_forward_and_rows_match_oracle(base, m, n, J, K, t):
@@ -47,7 +47,7 @@ def test_forward_and_rows_match_oracle(base, m, n, J, K, t):
     assert rel(rows64, orc.additive_rbf_dense(Z1[:9], Z2, c, J, K, base=base)) < 1e-12
 
 
-@pytest.mark.parametrize("base", [1, 2])
+@pytest.mark.parametrize("base", [1, 2, 3])
 @pytest.mark.parametrize("n,J,K,t", [(2000, 20, 1, 11), (1500, 26, 1, 16), (1300, 7, 3, 4), (1100, 1, 20, 11), (2500, 20, 5, 3), (1025, 40, 1, 1)])
 def test_symmetric_tensor_core_kernel_with_other_base_kernels(base, n, J, K, t):
     """square products of n >= 1024 rows go to the symmetric tcgen05 kernel for every base kernel (round 2): against the oracle (1e-5)
@@ -57,14 +57,15 @@ def test_symmetric_tensor_core_kernel_with_other_base_kernels(base, n, J, K, t):
     V = np.random.RandomState(n + t).randn(n, t).astype(np.float32)
     d = lambda a: torch.from_numpy(a).to(DEV)      # noqa: E731
     lay = _lib.plan_layout(J, K, base)
-    assert _lib.mvm_sym_supported(lay, t)
-    zp = _lib.pack_coords(d(Z), lay)
-    nlc = _lib.pack_log2c(d(c), lay)
-    got = _lib.mvm_sym(zp, lay, nlc, d(V)).cpu().numpy()
     ref = orc.kmv(Z, Z, c, J, K, V, base=base)
-    assert rel(got, ref) < 1e-5, rel(got, ref)
-    simt = _lib.mvm_fwd(zp, zp, lay, nlc, d(V)).cpu().numpy()
-    assert rel(got, simt) < 3e-6, rel(got, simt)
+    assert _lib.mvm_sym_supported(lay, t) == (base != 3 or K == 1)      # the cosine kernel with K > 1 takes the rectangular kernel
+    if _lib.mvm_sym_supported(lay, t):
+        zp = _lib.pack_coords(d(Z), lay)
+        nlc = _lib.pack_log2c(d(c), lay)
+        got = _lib.mvm_sym(zp, lay, nlc, d(V)).cpu().numpy()
+        assert rel(got, ref) < 1e-5, rel(got, ref)
+        simt = _lib.mvm_fwd(zp, zp, lay, nlc, d(V)).cpu().numpy()
+        assert rel(got, simt) < 3e-6, rel(got, simt)
     zt = d(Z)
     via_ops = ops.kmv_raw(zt, zt, d(c), J, K, d(V), base=base).cpu().numpy()              # the route the lazy operator takes
     assert rel(via_ops, ref) < 1e-5
@@ -85,7 +86,7 @@ def test_inverse_multiquadric_rows_match_reference_fixture():
         assert rel(got32, g["c%d_K" % idx]) < 2e-6
 
 
-@pytest.mark.parametrize("base", [1, 2])
+@pytest.mark.parametrize("base", [1, 2, 3])
 @pytest.mark.parametrize("n,J,K,t", [(500, 20, 1, 11), (300, 6, 4, 3), (260, 1, 20, 16)])
 def test_quadratic_form_gradients_match_oracle(base, n, J, K, t):
     Z1, Z2, c, _ = data(n, n + 37, J, K, t, seed=n + J + 10 * base)
@@ -106,7 +107,7 @@ def test_quadratic_form_gradients_match_oracle(base, n, J, K, t):
     assert rel(dZ1d.cpu().numpy(), r1) < 1e-9 and rel(dZ2d.cpu().numpy(), r2) < 1e-9 and rel(dcd.cpu().numpy(), rc) < 1e-9
 
 
-@pytest.mark.parametrize("kernel_type,base", [("Matern", 1), ("InverseMQ", 2)])
+@pytest.mark.parametrize("kernel_type,base", [("Matern", 1), ("InverseMQ", 2), ("Cosine", 3)])
 def test_kernel_classes_lower_to_the_fused_operator(kernel_type, base):
     """create_additive_rp_kernel(kernel_type=...) (training_routines.py:131-189): the operator carries the base kernel, its dense
     evaluation equals the closed form, and MLL + gradients in FP32 (fused kernels) agree with the FP64 path."""

@@ -1,5 +1,5 @@
 """Measurements for the 'next' rows of SURVEY §8(f) on one B200 (CUDA events, 3 warm-ups):
-  f4  forward K.V with the Matern-1.5 / inverse-multiquadric base kernels against RBF on the same SIMT kernel (cfg2 shape)
+  f4  forward K.V with the Matern-1.5 / inverse-multiquadric / cosine base kernels against RBF on the same SIMT kernel (cfg2 shape)
   f3  predictive variances: LOVE root (Lanczos steps) + variances of n* test points, and one exact batch of test points
 Prints one JSON line per measurement."""
 import json
@@ -38,7 +38,7 @@ def base_kernels(n=100_000, J=20, t=11):
     Z = torch.randn(n, J, generator=g).to(DEV)
     c = torch.full((J,), 0.05, device=DEV)
     V = torch.randn(n, t, generator=g).to(DEV)
-    for base, name in ((0, "rbf"), (1, "matern15"), (2, "inverse_mq")):
+    for base, name in ((0, "rbf"), (1, "matern15"), (2, "inverse_mq"), (3, "cosine")):
         p = ops.Packed(Z, J, 1, base)
         nlc = ops.pack_weights(c, p.lay)
         ms = timed(lambda: _lib.mvm_fwd(p.zp, p.zp, p.lay, nlc, V))
