@@ -23,8 +23,10 @@
 // copy per tile delivers a ready operand.  A chunk holds GT groups of KS = ceil(K/6) k-steps (GT*KS <= 4*NL, NL <= 2).
 //
 // CTA (one per SM, 24 warps):
-//   * 16 arithmetic warps in two teams of eight that take the tiles in turn (team = tile parity = S buffer): one team's exponentials
-//     fill the XU pipe while the other waits for its exponents, loads them, or splits and stores its S tile;
+//   * 16 arithmetic warps in two teams of eight that take the tiles in turn (team = tile parity = S buffer).  Measured (round 2,
+//     profiles/tcd_timeline_r02.txt): the teams run IN STEP -- they share the XU pipe during the exponentials and are in their
+//     hand-off code at the same time -- so that code is kept as short as it can be (precomputed toggling addresses, no S2R / LDC in
+//     the loops, the diagonal fix and the odd last batch in their own loop copies);
 //   * 4 epilogue warps (TMEM lane quadrants) for the column side;
 //   * 4 helper warps, one elected lane each (warp-uniform control flow: sym_tc_dev.cuh elect_one): the S-side MMAs (S.V then S^T.V of
 //     a tile), the bulk copies, and the distance MMAs of team 0's / team 1's tiles.  One distance issuer PER TEAM (round 2): with a
