@@ -146,16 +146,16 @@ struct LiveRun { int t, lim; };      // [t, lim): consecutive live tiles inside 
 struct Tile5Iter {
     int I, B, k_begin, ntiles;
     long long n;
-    __device__ __forceinline__ int block_of(int k) const { int Ip = I + k; return Ip >= B ? Ip - B : Ip; }
-    __device__ __forceinline__ bool offset_active(int k) const { return !((B % 2 == 0) && (k == B / 2) && (I >= B / 2)); }
-    __device__ __forceinline__ long long col0(int t) const { return (long long)block_of(k_begin + (t >> 2)) * T5_ROWS + (t & 3) * T5_BN; }
-    __device__ __forceinline__ bool live(int t) const { return offset_active(k_begin + (t >> 2)) && col0(t) < n; }
+    __host__ __device__ __forceinline__ int block_of(int k) const { int Ip = I + k; return Ip >= B ? Ip - B : Ip; }
+    __host__ __device__ __forceinline__ bool offset_active(int k) const { return !((B % 2 == 0) && (k == B / 2) && (I >= B / 2)); }
+    __host__ __device__ __forceinline__ long long col0(int t) const { return (long long)block_of(k_begin + (t >> 2)) * T5_ROWS + (t & 3) * T5_BN; }
+    __host__ __device__ __forceinline__ bool live(int t) const { return offset_active(k_begin + (t >> 2)) && col0(t) < n; }
     // (offsets k stay below B: half = B / 2 + 1 <= B, so block_of(k) == I exactly when k == 0)
-    __device__ __forceinline__ bool diag(int t) const { return k_begin + (t >> 2) == 0; }
-    __device__ __forceinline__ int next_live(int t) const { while (t < ntiles && !live(t)) ++t; return t; }
+    __host__ __device__ __forceinline__ bool diag(int t) const { return k_begin + (t >> 2) == 0; }
+    __host__ __device__ __forceinline__ int next_live(int t) const { while (t < ntiles && !live(t)) ++t; return t; }
     // the same enumeration with the liveness test paid once per block instead of once per tile (a tile's neighbours in its block
     // are live up to the first column >= n): advance() is an increment and a compare for three tiles out of four
-    __device__ __forceinline__ LiveRun run_from(int t) const {
+    __host__ __device__ __forceinline__ LiveRun run_from(int t) const {
         LiveRun r;
         r.t = next_live(t);
         r.lim = r.t;
@@ -166,8 +166,8 @@ struct Tile5Iter {
         }
         return r;
     }
-    __device__ __forceinline__ LiveRun first_run() const { return run_from(0); }
-    __device__ __forceinline__ void advance(LiveRun& r) const {
+    __host__ __device__ __forceinline__ LiveRun first_run() const { return run_from(0); }
+    __host__ __device__ __forceinline__ void advance(LiveRun& r) const {
         if (++r.t >= r.lim) r = run_from(r.t);
     }
 };
