@@ -91,7 +91,7 @@ def test_cosine_kernel_is_gpytorchs_cosine_kernel():
 
 def test_cosine_argument_reduction_in_a_float32_model():
     """kv_kernels.cuh::reduce_2pi restated in float32 (one rounding per FMA): n = round(d / 2 pi) by the 1.5 * 2^23 constant, then a
-    two-term Cody-Waite subtraction of n * 2 pi.  The reduced argument stays within [-pi, pi] (+ one ulp) and its cosine is the
+    two-term Cody-Waite subtraction of n * 2 pi.  The reduced argument stays within [-pi, pi] (to 1e-3) and its cosine is the
     cosine of d to 1.1e-7 for arguments up to 3000 -- far inside the 1e-5 of the K.V parity, with cos.approx's 2^-20.9 on top."""
     def fma(a, b, c):
         return np.float32(np.float64(a) * np.float64(b) + np.float64(c))
@@ -102,7 +102,7 @@ def test_cosine_argument_reduction_in_a_float32_model():
     assert np.all(n == np.rint(n)) and np.abs(n - d.astype(np.float64) / (2 * np.pi)).max() <= 0.5 + 1e-3
     r = fma(n, np.float32(-6.2831854820251465), d)
     r = fma(n, np.float32(1.7484555314695172e-07), r)
-    assert np.abs(r).max() < np.pi + 1e-5
+    assert np.abs(r).max() < np.pi + 1e-3        # (a hair over pi when d / 2 pi rounds the other way: harmless)
     err = np.abs(np.cos(r.astype(np.float64)) - np.cos(d.astype(np.float64)))
     assert err.max() < 1.5e-7, err.max()
     assert abs((6.2831854820251465 - 1.7484555314695172e-07) - 2 * np.pi) < 1e-14      # the split of 2 pi itself
