@@ -52,7 +52,13 @@ namespace {
 using namespace tcdev;
 
 constexpr int D_F = 4;            // tiles accumulated in TMEM per row-side epoch
-constexpr int D_ZST = 3;          // B-image stages
+#ifndef TCD_ZST
+#define TCD_ZST 3
+#endif
+constexpr int D_ZST = TCD_ZST;    // B-image stages.  With an EVEN number a stage only ever holds tiles of one team, and a distance issuer no
+                                  // longer has to walk through the other team's B-image barrier phases -- the one wait of this kernel
+                                  // that can alias under unbounded starvation of a helper warp (tests/test_tcd_protocol_cpu.py).
+                                  // -DTCD_ZST=4 costs NL x 8 KB of shared memory; not yet measured on a GPU, hence not the default.
 constexpr int D_AW = 16;          // arithmetic warps
 constexpr int D_FC = 4;            // right-hand-side columns folded per arithmetic thread (16 warps: 4 lane quadrants x 4 column parts)
 constexpr int D_NDI = 2;          // distance-MMA issuing warps (one per team)
@@ -90,17 +96,17 @@ constexpr uint32_t D_TM_D1 = 0, D_TM_D2 = 64, D_TM_A = 128, D_TM_D0 = 256;
 static_assert(D_TM_D0 + 2 * D_NBUF * 64 <= 512, "TMEM columns");
 
 // barrier indices (32 x 8 bytes)
-constexpr int BD_ZFULL = 0;      // [3]  bulk copy of a B image -> distance issuers
-constexpr int BD_ZFREE = 3;      // [3]  tcgen05.commit of the tile's distance issuer: the B image has been consumed
-constexpr int BD_BFULL = 6;      // [4]  bulk copy -> S-side issuer (B tile of V)
-constexpr int BD_SFULL = 10;     // [2]  the tile's team -> S-side issuer (count 8)
-constexpr int BD_TDONE = 12;     // [2]  tcgen05.commit of the S-side issuer after a tile's row-side and column-side MMAs
-constexpr int BD_EREAD = 14;     // [2]  epilogue warps have read D2 (count 4)
-constexpr int BD_D1EMPTY = 16;   // [2]  arithmetic warps have folded an epoch of D1 (count 16)
-constexpr int BD_BCFULL = 18;    // [1]  bulk copy of the column-side B operand
-constexpr int BD_AFULL = 19;     // [1]  the A image is in tensor memory (count 4: the warps of rows 0..127)
-constexpr int BD_D0FULL = 20;    // [2 teams][D_NBUF]  tcgen05.commit of the team's distance issuer for a batch of two groups
-constexpr int BD_D0FREE = 20 + 2 * D_NBUF;   // [2 teams][D_NBUF]  the team's warps have read the batch (count 8)
+constexpr int BD_ZFULL = 0;                    // [D_ZST]  bulk copy of a B image -> distance issuers
+constexpr int BD_ZFREE = BD_ZFULL + D_ZST;     // [D_ZST]  tcgen05.commit of the tile's distance issuer: the B image has been consumed
+constexpr int BD_BFULL = BD_ZFREE + D_ZST;     // [D_BST]  bulk copy -> S-side issuer (B tile of V)
+constexpr int BD_SFULL = BD_BFULL + D_BST;     // [2]  the tile's team -> S-side issuer (count 8)
+constexpr int BD_TDONE = BD_SFULL + 2;         // [2]  tcgen05.commit of the S-side issuer after a tile's row-side and column-side MMAs
+constexpr int BD_EREAD = BD_TDONE + 2;         // [2]  epilogue warps have read D2 (count 4)
+constexpr int BD_D1EMPTY = BD_EREAD + 2;       // [2]  arithmetic warps have folded an epoch of D1 (count 16)
+constexpr int BD_BCFULL = BD_D1EMPTY + 2;      // [1]  bulk copy of the column-side B operand
+constexpr int BD_AFULL = BD_BCFULL + 1;        // [1]  the A image is in tensor memory (count 4: the warps of rows 0..127)
+constexpr int BD_D0FULL = BD_AFULL + 1;        // [2 teams][D_NBUF]  tcgen05.commit of the team's distance issuer for a batch of two groups
+constexpr int BD_D0FREE = BD_D0FULL + 2 * D_NBUF;   // [2 teams][D_NBUF]  the team's warps have read the batch (count 8)
 static_assert(BD_D0FREE + 2 * D_NBUF <= 32, "barrier block is 256 bytes");
 #ifndef TCD_FENCE_ISSUER
 #define TCD_FENCE_ISSUER 0       // 0: every arithmetic warp fences its S stores (generic -> async proxy) before SFULL; 1 (experiment,
@@ -638,6 +644,7 @@ __global__ void __maxnreg__(D_REGS_LAUNCH) mvm_sym_tcd_kernel(const SymDArgs a) 
             uint32_t ibuf = 0, iuse = 0;       // this team's (tile, batch) counter modulo / divided by D_NBUF
             for (int t = it.next_live(0); t < it.ntiles; t = it.next_live(t + 1), ++jd) {
                 const int zs = jd % D_ZST;
+                if (D_ZST % 2 == 0 && (jd & 1) != w) continue;      // (even stage count: the other team's tiles never use this team's stages)
                 mbar_wait_ns(a.sleep_ns, &bars[BD_ZFULL + zs], (uint32_t)((jd / D_ZST) & 1));
                 if ((jd & 1) != w) continue;
                 tc5_fence_after();

@@ -47,7 +47,7 @@ def wait(bar, idx):
     return ("wait", bar, idx)
 
 
-def roles(L, NB):
+def roles(L, NB, ZST=ZST):
     """the roles of one CTA with L live tiles and NB batches per tile; returns (barriers, {name: generator})"""
     B = {}
     for s in range(ZST):
@@ -147,6 +147,8 @@ def roles(L, NB):
         yield wait(B["AFULL"], 0)
         ibuf = iuse = 0
         for jd in range(L):
+            if ZST % 2 == 0 and jd % 2 != w:                   # -DTCD_ZST=4: a stage holds tiles of one team only, no walk-through
+                continue
             yield wait(B["ZFULL%d" % (jd % ZST)], jd // ZST)
             if jd % 2 != w:
                 continue
@@ -173,12 +175,12 @@ def roles(L, NB):
     return B, agents
 
 
-def simulate(L, NB, seed, slow=(), max_bypass=None):
+def simulate(L, NB, seed, slow=(), max_bypass=None, zst=ZST):
     """random schedule; agents whose name starts with one of `slow` are picked 50 times less often, but (max_bypass) no agent that
     can run is passed over for more than that many steps; asynchronous completions (commits in issue order per issuer, loads in any
     order) fire with probability 1/4 per step"""
     rng = random.Random(seed)
-    B, agents = roles(L, NB)
+    B, agents = roles(L, NB, zst)
     blocked = {}                   # name -> pending op
     queues = {"S": [], "D0": [], "D1": []}
     loads = []
@@ -266,3 +268,9 @@ def test_unbounded_starvation_of_a_helper_warp_would_alias_a_parity_wait():
         with pytest.raises(AssertionError, match=r"wait on %s\d for completion \d+ issued at phase" % barrier):
             for seed in range(20):
                 simulate(7, 1, 1000 + seed, slow=slow)
+    # four B-image stages (the -DTCD_ZST=4 build): the distance issuers' case is gone, whatever the starvation
+    for slow in (("D0",), ("D1",), ("D",)):
+        for NB in (1, 2, 4):
+            for L in (1, 4, 7, 12, 13):
+                for seed in range(4):
+                    simulate(L, NB, 2000 + seed, slow=slow, zst=4)
