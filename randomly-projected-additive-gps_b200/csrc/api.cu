@@ -251,7 +251,7 @@ int rpgp_mvm_sym_f32(const float* zp, int64_t n, const rpgp_layout* lay, const f
                      float* out, int ldo, int row_block_begin, int row_block_end, void* workspace, size_t workspace_bytes,
                      void* stream) {
     if (int rc = check_layout(lay)) return rc;
-    RPGP_REQUIRE(rpgp_mvm_sym_supported(lay, t), "mvm_sym: needs 1 <= t <= 16 right-hand sides per call (got t=%d)", t);
+    RPGP_REQUIRE(rpgp_mvm_sym_supported(lay, t), "mvm_sym: needs 1 <= t <= 16 right-hand sides per call (got t=%d) and a layout the symmetric kernel takes (base %d, KP %d: see rpgp_mvm_sym_supported)", t, lay ? lay->base : -1, lay ? lay->KP : -1);
     RPGP_REQUIRE(n >= 1 && ldo >= t, "mvm_sym: n=%lld ldo=%d", (long long)n, ldo);
     RPGP_REQUIRE(zp && neg_log2c && Vp16 && out, "mvm_sym: NULL pointer");
     RPGP_REQUIRE(aligned16(zp) && aligned16(Vp16), "mvm_sym: operands must be 16-byte aligned");
